@@ -1,0 +1,188 @@
+// extern "C" entry points of libcurvegs.so (see include/curvegs.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace cg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
+                    const float* scales, const float* rotations, const float* cov3D_precomp,
+                    int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st);
+int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
+                     void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
+                     float* out_map, cudaStream_t st);
+int launch_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* means3D, const float* opacities,
+               const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+               const void* geom, const void* img, const void* bin_keep, const float* dL_dcolor,
+               const float* dL_dinvdepth, const float* dL_dall_map, void* grad_scratch, float* dL_dmeans2D,
+               float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+               float* dL_drotations, float* dL_dall_map_in, cudaStream_t st);
+int launch_mark_visible(int64_t P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t st);
+
+static int check_settings(const cg_raster_settings* s) {
+  CG_ARG(s != nullptr, "settings");
+  CG_ARG(s->image_width > 0 && s->image_height > 0, "image size");
+  CG_ARG(s->image_width <= 65535 * TILE_X && s->image_height <= 65535 * TILE_Y, "image too large for packed tile rects");
+  CG_ARG(s->bg && s->viewmatrix && s->projmatrix, "bg/viewmatrix/projmatrix must be device pointers");
+  return CG_OK;
+}
+
+}  // namespace cg
+
+using namespace cg;
+
+extern "C" {
+
+int cg_abi_version(void) { return 1; }
+const char* cg_last_error(void) { return g_err; }
+
+size_t cg_raster_geom_bytes(int64_t P) {
+  size_t b = 0;
+  GeomState::carve(nullptr, P < 0 ? 0 : P, &b);
+  return b;
+}
+size_t cg_raster_img_bytes(int32_t W, int32_t H) {
+  size_t b = 0;
+  ImgState::carve(nullptr, W, H, &b);
+  return b;
+}
+size_t cg_raster_bin_keep_bytes(int64_t R) {
+  size_t b = 0;
+  BinKeep::carve(nullptr, R < 0 ? 0 : R, &b);
+  return b;
+}
+size_t cg_raster_bin_scratch_bytes(int64_t R) {
+  size_t b = 0;
+  BinScratch::carve(nullptr, R < 0 ? 0 : R, &b);
+  return b;
+}
+size_t cg_raster_bwd_scratch_bytes(int64_t P) { return size_t(P < 1 ? 1 : P) * 8 * sizeof(float); }
+
+int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
+                       const float* scales, const float* rotations, const float* cov3D_precomp, int32_t* radii,
+                       void* geom, size_t geom_bytes, int64_t* num_rendered, void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  CG_ARG(num_rendered != nullptr, "num_rendered");
+  *num_rendered = 0;
+  if (P == 0) return CG_OK;
+  CG_ARG(P > 0 && P < (int64_t(1) << 31), "P");
+  CG_ARG(means3D && opacities && radii && geom, "means3D/opacities/radii/geom");
+  CG_ARG((scales && rotations && !cov3D_precomp) || (!scales && !rotations && cov3D_precomp),
+         "exactly one of scale/rotation pair or precomputed 3D covariance");
+  if (geom_bytes < cg_raster_geom_bytes(P)) {
+    set_error("geom buffer too small: %zu < %zu", geom_bytes, cg_raster_geom_bytes(P));
+    return CG_ERR_CAPACITY;
+  }
+  CG_ARG((reinterpret_cast<uintptr_t>(geom) & 127u) == 0, "geom must be 128-byte aligned");
+  return launch_fwd_geom(s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, geom, num_rendered,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
+                        void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color,
+                        float* out_invdepth, float* out_all_map, void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  CG_ARG(P >= 0 && R >= 0, "P/R");
+  CG_ARG(img && out_color && out_invdepth, "img/out_color/out_invdepth");
+  CG_ARG(!s->render_geo || out_all_map, "out_all_map required with render_geo");
+  CG_ARG((reinterpret_cast<uintptr_t>(img) & 127u) == 0, "img must be 128-byte aligned");
+  if (R > 0) {
+    CG_ARG(geom && bin_keep && bin_scratch && colors, "geom/bin_keep/bin_scratch/colors");
+    CG_ARG(!s->render_geo || all_map, "all_map required with render_geo");
+    CG_ARG((reinterpret_cast<uintptr_t>(bin_keep) & 127u) == 0 && (reinterpret_cast<uintptr_t>(bin_scratch) & 127u) == 0,
+           "bin buffers must be 128-byte aligned");
+    CG_ARG(!all_map || (reinterpret_cast<uintptr_t>(all_map) & 15u) == 0, "all_map must be 16-byte aligned");
+  }
+  return launch_fwd_blend(s, P, R, colors, all_map, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
+                          out_all_map, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cg_raster_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* means3D, const float* opacities,
+                  const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                  const void* geom, const void* img, const void* bin_keep, const float* dL_dcolor,
+                  const float* dL_dinvdepth, const float* dL_dall_map, void* grad_scratch, float* dL_dmeans2D,
+                  float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* dL_dall_map_in, void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  if (P == 0) return CG_OK;
+  CG_ARG(P > 0 && R >= 0, "P/R");
+  CG_ARG(means3D && opacities && radii && geom && img && dL_dcolor && grad_scratch, "inputs");
+  CG_ARG(R == 0 || bin_keep, "bin_keep");
+  CG_ARG((scales && rotations && !cov3D_precomp) || (!scales && !rotations && cov3D_precomp),
+         "exactly one of scale/rotation pair or precomputed 3D covariance");
+  CG_ARG(dL_dmeans2D && dL_dcolors && dL_dopacity && dL_dmeans3D, "gradient outputs");
+  CG_ARG(cov3D_precomp || (dL_dscales && dL_drotations), "dL_dscales/dL_drotations");
+  CG_ARG((reinterpret_cast<uintptr_t>(grad_scratch) & 31u) == 0, "grad_scratch must be 32-byte aligned");
+  return launch_bwd(s, P, R, means3D, opacities, scales, rotations, cov3D_precomp, radii, geom, img, bin_keep,
+                    dL_dcolor, dL_dinvdepth, dL_dall_map, grad_scratch, dL_dmeans2D, dL_dcolors, dL_dopacity,
+                    dL_dmeans3D, dL_dcov3D, dL_dscales, dL_drotations, dL_dall_map_in,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cg_mark_visible(int64_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, void* stream) {
+  (void)projmatrix;
+  if (P == 0) return CG_OK;
+  CG_ARG(P > 0 && means3D && viewmatrix && present, "mark_visible inputs");
+  return launch_mark_visible(P, means3D, viewmatrix, present, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H, const void* geom, const void* img,
+                          const void* bin_keep, const void* bin_scratch, void* dst, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CG_ARG(dst != nullptr, "dst");
+  const size_t tiles = size_t((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  GeomState g = GeomState::carve(const_cast<void*>(geom), P, nullptr);
+  ImgState im = ImgState::carve(const_cast<void*>(img), W, H, nullptr);
+  BinKeep bk = BinKeep::carve(const_cast<void*>(bin_keep), R, nullptr);
+  BinScratch bs = BinScratch::carve(const_cast<void*>(bin_scratch), R, nullptr);
+  switch (which) {
+    case 0: {
+      int passes = (32 + int(tile_key_bits(uint32_t(tiles))) + 7) / 8;
+      if (passes > SORT_MAX_PASSES) passes = SORT_MAX_PASSES;
+      CG_ARG(bin_scratch != nullptr, "bin_scratch");
+      src = bs.keys[passes & 1]; bytes = size_t(R) * 8; break;
+    }
+    case 1: CG_ARG(bin_keep != nullptr, "bin_keep"); src = bk.point_list; bytes = size_t(R) * 4; break;
+    case 2: src = im.ranges; bytes = tiles * 8; break;
+    case 3: src = g.tiles; bytes = size_t(P) * 4; break;
+    case 4: src = g.xy; bytes = size_t(P) * 8; break;
+    case 5: src = g.depth; bytes = size_t(P) * 4; break;
+    case 6: src = g.conic_o; bytes = size_t(P) * 16; break;
+    case 7: src = im.n_contrib; bytes = size_t(W) * H * 4; break;
+    case 8: src = im.final_T; bytes = size_t(W) * H * 4; break;
+    default: set_error("debug_fetch: unknown selector %d", which); return CG_ERR_ARG;
+  }
+  CG_ARG(src != nullptr, "state buffer");
+  if (bytes) CG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return CG_OK;
+}
+
+}  // extern "C"
+
+// ---- TEMPORARY stubs until sample.cu / ssim.cu / knn.cu land (removed in the same round) ----
+#ifndef CG_HAVE_SAMPLE
+extern "C" {
+size_t cg_sample_scratch_bytes(int64_t, int32_t) { return 0; }
+int cg_sample_fwd(int64_t, int32_t, const float*, const float*, const uint8_t*, const float*, float, float*, float*, float*, float*, void*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
+int cg_sample_bwd(int64_t, int32_t, const float*, const float*, const uint8_t*, const float*, float, const float*, const float*, const float*, const float*, float*, float*, void*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
+int cg_ssim_fwd(int32_t, int32_t, int32_t, int32_t, float, float, const float*, const float*, float*, float*, float*, float*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
+int cg_ssim_bwd(int32_t, int32_t, int32_t, int32_t, float, float, const float*, const float*, const float*, const float*, const float*, const float*, float*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
+size_t cg_knn_scratch_bytes(int64_t) { return 0; }
+int cg_knn_mean_dist2(int64_t, const float*, float*, void*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
+}
+#endif

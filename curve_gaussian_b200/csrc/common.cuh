@@ -1,0 +1,168 @@
+// Shared helpers for libcurvegs (sm_100a). No torch headers anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include "../../include/curvegs.h"
+
+namespace cg {
+
+constexpr int TILE_X = 16;   // reference config.h:17-18 (BLOCK_X/BLOCK_Y)
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+
+void set_error(const char* fmt, ...);
+
+#define CG_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      cg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,             \
+                    cudaGetErrorString(_e));                                 \
+      return CG_ERR_CUDA;                                                    \
+    }                                                                        \
+  } while (0)
+
+#define CG_LAUNCH_CHECK(debug, stream)                                       \
+  do {                                                                       \
+    CG_CUDA(cudaGetLastError());                                             \
+    if (debug) CG_CUDA(cudaStreamSynchronize(stream));                       \
+  } while (0)
+
+#define CG_ARG(cond, msg)                                                    \
+  do {                                                                       \
+    if (!(cond)) {                                                           \
+      cg::set_error("bad argument: %s (%s)", msg, #cond);                    \
+      return CG_ERR_ARG;                                                     \
+    }                                                                        \
+  } while (0)
+
+// Carve 128-byte aligned typed arrays out of one caller-owned byte blob
+// (same idea as rasterizer_impl.h:21-27, but sizes are computed with the very
+// same walk so size query and carving cannot disagree).
+struct Carver {
+  char* p;
+  size_t used;
+  explicit Carver(void* base) : p(reinterpret_cast<char*>(base)), used(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t off = (used + 127) & ~size_t(127);
+    used = off + count * sizeof(T);
+    return p ? reinterpret_cast<T*>(p + off) : nullptr;
+  }
+};
+
+// One sorted tile-instance, staged into shared memory by a bulk async copy.
+// 48 bytes = 3 x 16B, so any run of records is a legal cp.async.bulk span.
+struct __align__(16) Rec {
+  float x, y;          // pixel-space mean           (geomState.means2D)
+  float ca, cb;        // conic xx, xy
+  float cc, o;         // conic yy, opacity          (geomState.conic_opacity)
+  float col, invd;     // colour (1 channel), 1/depth
+  float m0, m1, m2, m3;// all_map channels
+};
+static_assert(sizeof(Rec) == 48, "record must stay 48 bytes");
+
+struct GeomState {
+  float2* xy;
+  float4* conic_o;
+  float* depth;
+  uint32_t* tiles;
+  uint2* rect;       // packed tile rect: x = min.x | min.y<<16, y = max.x | max.y<<16
+  uint32_t* blk_sum;
+  uint32_t* blk_prefix;
+  uint32_t* total;   // [0] = R
+  static GeomState carve(void* base, int64_t P, size_t* bytes) {
+    Carver c(base);
+    GeomState g;
+    int64_t nblk = (P + 255) / 256;
+    g.xy = c.take<float2>(P);
+    g.conic_o = c.take<float4>(P);
+    g.depth = c.take<float>(P);
+    g.tiles = c.take<uint32_t>(P);
+    g.rect = c.take<uint2>(P);
+    g.blk_sum = c.take<uint32_t>(nblk);
+    g.blk_prefix = c.take<uint32_t>(nblk);
+    g.total = c.take<uint32_t>(32);
+    if (bytes) *bytes = (c.used + 127) & ~size_t(127);
+    return g;
+  }
+};
+
+struct ImgState {
+  float* final_T;
+  uint32_t* n_contrib;
+  uint2* ranges;
+  uint32_t* tile_maxc;  // per tile: max n_contrib over its pixels (backward start)
+  static ImgState carve(void* base, int W, int H, size_t* bytes) {
+    Carver c(base);
+    ImgState s;
+    size_t npix = size_t(W) * H;
+    size_t tiles = size_t((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+    s.final_T = c.take<float>(npix);
+    s.n_contrib = c.take<uint32_t>(npix);
+    s.ranges = c.take<uint2>(tiles);
+    s.tile_maxc = c.take<uint32_t>(tiles);
+    if (bytes) *bytes = (c.used + 127) & ~size_t(127);
+    return s;
+  }
+};
+
+struct BinKeep {
+  Rec* rec;
+  uint32_t* point_list;
+  static BinKeep carve(void* base, int64_t R, size_t* bytes) {
+    Carver c(base);
+    BinKeep b;
+    b.rec = c.take<Rec>(R + 1);
+    b.point_list = c.take<uint32_t>(R + 1);
+    if (bytes) *bytes = (c.used + 127) & ~size_t(127);
+    return b;
+  }
+};
+
+// Radix sort geometry (see sort.cu).
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
+constexpr int SORT_MAX_PASSES = 8;
+
+struct BinScratch {
+  uint64_t* keys[2];
+  uint32_t* vals[2];
+  uint32_t* hist;     // [SORT_MAX_PASSES][256] global digit histograms -> exclusive bases
+  uint32_t* ticket;   // [SORT_MAX_PASSES] dynamic tile id counters
+  uint32_t* status;   // [passes][ntiles][256] decoupled look-back words
+  size_t status_words;
+  static BinScratch carve(void* base, int64_t R, size_t* bytes) {
+    Carver c(base);
+    BinScratch b;
+    int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
+    b.keys[0] = c.take<uint64_t>(R + 1);
+    b.keys[1] = c.take<uint64_t>(R + 1);
+    b.vals[0] = c.take<uint32_t>(R + 1);
+    b.vals[1] = c.take<uint32_t>(R + 1);
+    b.hist = c.take<uint32_t>(SORT_MAX_PASSES * 256);
+    b.ticket = c.take<uint32_t>(32);
+    b.status_words = size_t(SORT_MAX_PASSES) * size_t(ntiles > 0 ? ntiles : 1) * 256;
+    b.status = c.take<uint32_t>(b.status_words);
+    if (bytes) *bytes = (c.used + 127) & ~size_t(127);
+    return b;
+  }
+};
+
+// Number of tile-index bits that take part in the sort. The reference finds it
+// with a halving search (rasterizer_impl.cu:35-50, getHigherMsb) whose result
+// is the bit length of n for n >= 1 and 1 for n == 0; bits above it are zero
+// in every key, so the sorted order does not depend on this being tight.
+inline uint32_t tile_key_bits(uint32_t n) {
+  uint32_t bits = 0;
+  while (n) { ++bits; n >>= 1; }
+  return bits ? bits : 1;
+}
+
+int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
+                     bool debug, cudaStream_t stream);
+
+}  // namespace cg

@@ -1,0 +1,436 @@
+// Forward rasterization kernels: EWA preprocess (+tile counts, block sums),
+// block-sum scan, key emission, tile ranges, sorted-record gather, and the
+// per-tile front-to-back blend fed by TMA bulk copies.
+//
+// Reference behaviour followed (semantics, not structure):
+//   preprocess   forward.cu:155-274, auxiliary.h:40-55,151-176
+//   scan + R     rasterizer_impl.cu:283-287
+//   key emission rasterizer_impl.cu:70-111
+//   ranges       rasterizer_impl.cu:116-138
+//   blend        forward.cu:279-417
+#include "common.cuh"
+#include "math.cuh"
+
+namespace cg {
+
+// ---------------------------------------------------------------------------
+// Stage `n` consecutive floats (n <= capacity of sm) with 128-bit loads.
+__device__ __forceinline__ void stage_floats(const float* __restrict__ src, float* sm, int n) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<float4*>(sm)[i] = __ldg(s4 + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) sm[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = __ldg(src + i);
+  }
+}
+
+__device__ __forceinline__ float ndc_to_pix(float v, int S) {
+  // double arithmetic on purpose: the reference's literals are doubles (auxiliary.h:40-43)
+  return float(((double(v) + 1.0) * double(S) - 1.0) * 0.5);
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __restrict__ opacities,
+               const float* __restrict__ scales, const float* __restrict__ rotations,
+               const float* __restrict__ cov3D_precomp, float scale_modifier,
+               const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
+               int W, int H, float tanx, float tany, float fx, float fy, int grid_x, int grid_y,
+               int antialiasing, int32_t* __restrict__ radii, GeomState g) {
+  __shared__ __align__(16) float s_mean[768];
+  __shared__ __align__(16) float s_scale[768];
+  __shared__ float s_vm[16], s_pm[16];
+  __shared__ uint32_t s_wsum[8];
+
+  const int64_t blk0 = int64_t(blockIdx.x) * 256;
+  const int nhere = int(P - blk0 < 256 ? P - blk0 : 256);
+  stage_floats(means3D + blk0 * 3, s_mean, nhere * 3);
+  if (scales) stage_floats(scales + blk0 * 3, s_scale, nhere * 3);
+  if (threadIdx.x < 16) s_vm[threadIdx.x] = viewmatrix[threadIdx.x];
+  else if (threadIdx.x < 32) s_pm[threadIdx.x - 16] = projmatrix[threadIdx.x - 16];
+  __syncthreads();
+
+  const int64_t idx = blk0 + threadIdx.x;
+  uint32_t touched = 0;
+  int radius_out = 0;
+  if (idx < P) {
+    const float px = s_mean[3 * threadIdx.x], py = s_mean[3 * threadIdx.x + 1], pz = s_mean[3 * threadIdx.x + 2];
+    const float3 p_view = xform43(px, py, pz, s_vm);
+    if (!(p_view.z <= 0.2f)) {  // near cull only, no x/y frustum test (auxiliary.h:166)
+      const float4 p_hom = xform44(px, py, pz, s_pm);
+      const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+      const float ndc_x = p_hom.x * p_w, ndc_y = p_hom.y * p_w;
+
+      float cov6[6];
+      if (cov3D_precomp) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cov6[i] = cov3D_precomp[idx * 6 + i];
+      } else {
+        float4 q;
+        if ((reinterpret_cast<uintptr_t>(rotations) & 15u) == 0) q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+        else q = make_float4(rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2], rotations[4 * idx + 3]);
+        cov3d_from_scale_rot(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1], s_scale[3 * threadIdx.x + 2],
+                             scale_modifier, q, cov6);
+      }
+      Proj2D pr = project_cov(px, py, pz, fx, fy, tanx, tany, cov6, s_vm);
+      float3 cov = pr.cov;
+      constexpr float h_var = 0.3f;
+      const float det_cov = cov.x * cov.z - cov.y * cov.y;
+      cov.x += h_var;
+      cov.z += h_var;
+      const float det = cov.x * cov.z - cov.y * cov.y;
+      float h_scaling = 1.0f;
+      if (antialiasing) h_scaling = sqrtf(fmaxf(0.000025f, det_cov / det));
+      if (det != 0.0f) {
+        const float det_inv = 1.f / det;
+        const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+        const float mid = 0.5f * (cov.x + cov.z);
+        const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+        const float pix_x = ndc_to_pix(ndc_x, W), pix_y = ndc_to_pix(ndc_y, H);
+        const int rad = int(my_radius);
+        // tile rectangle (auxiliary.h:45-55); int() truncates toward zero
+        const int mnx = min(grid_x, max(0, int((pix_x - rad) / TILE_X)));
+        const int mny = min(grid_y, max(0, int((pix_y - rad) / TILE_Y)));
+        const int mxx = min(grid_x, max(0, int((pix_x + rad + TILE_X - 1) / TILE_X)));
+        const int mxy = min(grid_y, max(0, int((pix_y + rad + TILE_Y - 1) / TILE_Y)));
+        const uint32_t area = uint32_t(mxx - mnx) * uint32_t(mxy - mny);
+        if (area != 0) {
+          touched = area;
+          radius_out = rad;
+          g.depth[idx] = p_view.z;
+          g.xy[idx] = make_float2(pix_x, pix_y);
+          g.conic_o[idx] = make_float4(conic.x, conic.y, conic.z, __ldg(opacities + idx) * h_scaling);
+          g.rect[idx] = make_uint2(uint32_t(mnx) | (uint32_t(mny) << 16), uint32_t(mxx) | (uint32_t(mxy) << 16));
+        }
+      }
+    }
+    radii[idx] = radius_out;
+    g.tiles[idx] = touched;
+  }
+  // block sum of tiles_touched -> blk_sum
+  uint32_t v = touched;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < 8; ++i) t += s_wsum[i];
+    g.blk_sum[blockIdx.x] = t;
+  }
+}
+
+// Single CTA: exclusive scan of the per-block sums, total -> g.total[0].
+__global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState g) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nblk; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    uint32_t v = (i < nblk) ? g.blk_sum[i] : 0u;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t x = s_w[lane], xi = x;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, xi, o);
+        if (lane >= o) xi += n;
+      }
+      s_w[lane] = xi - x;  // exclusive warp base
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    if (i < nblk) g.blk_prefix[i] = carry + s_w[w] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_w[w] + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) g.total[0] = s_carry;
+}
+
+// One (key,value) per overlapped tile, row-major over the rect, key =
+// tile<<32 | float_bits(depth) (rasterizer_impl.cu:70-111).
+__global__ void __launch_bounds__(256)
+emit_keys(int64_t P, GeomState g, int grid_x, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  __shared__ uint32_t s_w[8];
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t cnt = (idx < P) ? g.tiles[idx] : 0u;
+  uint32_t inc = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  uint32_t off = g.blk_prefix[blockIdx.x] + inc - cnt;
+  for (uint32_t i = 0; i < w; ++i) off += s_w[i];
+  if (cnt == 0) return;
+  const uint2 rc = g.rect[idx];
+  const uint32_t mnx = rc.x & 0xffffu, mny = rc.x >> 16, mxx = rc.y & 0xffffu, mxy = rc.y >> 16;
+  const uint32_t dbits = __float_as_uint(g.depth[idx]);
+  for (uint32_t y = mny; y < mxy; ++y)
+    for (uint32_t x = mnx; x < mxx; ++x) {
+      keys[off] = (uint64_t(y * uint32_t(grid_x) + x) << 32) | dbits;
+      vals[off] = uint32_t(idx);
+      ++off;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_ranges(int64_t R, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= R) return;
+  const uint32_t cur = uint32_t(keys[i] >> 32);
+  if (i == 0) ranges[cur].x = 0;
+  else {
+    const uint32_t prev = uint32_t(keys[i - 1] >> 32);
+    if (cur != prev) { ranges[prev].y = uint32_t(i); ranges[cur].x = uint32_t(i); }
+  }
+  if (i == R - 1) ranges[cur].y = uint32_t(R);
+}
+
+// Sorted instance i -> contiguous 48-byte record + point list entry.
+__global__ void __launch_bounds__(256)
+gather_records(int64_t R, const uint32_t* __restrict__ sorted_vals, GeomState g,
+               const float* __restrict__ colors, const float* __restrict__ all_map,
+               Rec* __restrict__ rec, uint32_t* __restrict__ point_list) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= R) return;
+  const uint32_t id = sorted_vals[i];
+  point_list[i] = id;
+  const float2 xy = g.xy[id];
+  const float4 co = g.conic_o[id];
+  float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (all_map) mp = __ldg(reinterpret_cast<const float4*>(all_map) + id);
+  float4* out = reinterpret_cast<float4*>(rec + i);
+  out[0] = make_float4(xy.x, xy.y, co.x, co.y);
+  out[1] = make_float4(co.z, co.w, __ldg(colors + id), 1.f / g.depth[id]);
+  out[2] = mp;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA) helpers.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int BATCH = 256;
+
+// One CTA per 16x16 tile, one thread per pixel. The tile's sorted records are a
+// contiguous span; thread 0 streams it into a 2-deep shared ring with
+// cp.async.bulk while all threads blend the previous batch.
+template <bool GEO>
+__global__ void __launch_bounds__(256)
+blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, int H,
+          const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
+          float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+          uint32_t* __restrict__ tile_maxc) {
+  __shared__ __align__(128) Rec s_rec[2][BATCH];
+  __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ uint32_t s_maxc;
+
+  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const uint32_t tid = threadIdx.y * TILE_X + threadIdx.x;
+  const uint32_t pix_x = blockIdx.x * TILE_X + threadIdx.x, pix_y = blockIdx.y * TILE_Y + threadIdx.y;
+  const bool inside = pix_x < uint32_t(W) && pix_y < uint32_t(H);
+  const uint32_t pix_id = uint32_t(W) * pix_y + pix_x;
+  const float pxf = float(pix_x), pyf = float(pix_y);
+  const uint2 range = ranges[tile];
+  const int total = int(range.y - range.x);
+  const int rounds = (total + BATCH - 1) / BATCH;
+
+  if (tid == 0) {
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_fence_init();
+    s_maxc = 0;
+  }
+  __syncthreads();
+  if (tid == 0 && rounds > 0) {
+    const uint32_t bytes = uint32_t(min(BATCH, total)) * uint32_t(sizeof(Rec));
+    mbar_expect_tx(&s_full[0], bytes);
+    bulk_g2s(&s_rec[0][0], rec + range.x, bytes, &s_full[0]);
+  }
+
+  bool done = !inside;
+  float T = 1.0f, C = 0.f, invd_acc = 0.f;
+  float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3v = 0.f;
+  uint32_t contributor = 0, last_contributor = 0;
+
+  int todo = total;
+  for (int b = 0; b < rounds; ++b, todo -= BATCH) {
+    const int num_done = __syncthreads_count(done);
+    if (num_done == TILE_PIX) {
+      // batch b is (or was) in flight: drain it before the CTA retires
+      if (tid == 0) mbar_wait(&s_full[b & 1], (b >> 1) & 1);
+      break;
+    }
+    if (tid == 0 && b + 1 < rounds) {
+      const int nb = min(BATCH, todo - BATCH);
+      const uint32_t bytes = uint32_t(nb) * uint32_t(sizeof(Rec));
+      mbar_expect_tx(&s_full[(b + 1) & 1], bytes);
+      bulk_g2s(&s_rec[(b + 1) & 1][0], rec + range.x + size_t(b + 1) * BATCH, bytes, &s_full[(b + 1) & 1]);
+    }
+    mbar_wait(&s_full[b & 1], (b >> 1) & 1);
+    const Rec* batch = s_rec[b & 1];
+    const int n = min(BATCH, todo);
+    for (int j = 0; !done && j < n; ++j) {
+      contributor++;
+      const float4 a = *reinterpret_cast<const float4*>(&batch[j].x);    // x y ca cb
+      const float2 c2 = *reinterpret_cast<const float2*>(&batch[j].cc);  // cc o
+      const float dx = a.x - pxf, dy = a.y - pyf;
+      const float power = -0.5f * (a.z * dx * dx + c2.x * dy * dy) - a.w * dx * dy;
+      if (power > 0.0f) continue;
+      const float alpha = fminf(0.99f, c2.y * expf(power));
+      if (alpha < 1.0f / 255.0f) continue;
+      const float test_T = T * (1 - alpha);
+      if (test_T < 0.0001f) { done = true; continue; }
+      const float2 ci = *reinterpret_cast<const float2*>(&batch[j].col);  // col invd
+      C += ci.x * alpha * T;
+      invd_acc += ci.y * alpha * T;
+      if (GEO) {
+        const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
+        M0 += mp.x * alpha * T;
+        M1 += mp.y * alpha * T;
+        M2 += mp.z * alpha * T;
+        M3v += mp.w * alpha * T;
+      }
+      T = test_T;
+      last_contributor = contributor;
+    }
+  }
+
+  if (inside) {
+    final_T[pix_id] = T;
+    n_contrib[pix_id] = last_contributor;
+    out_color[pix_id] = C + T * bg[0];
+    out_invd[pix_id] = invd_acc;
+    if (GEO) {
+      const size_t hw = size_t(H) * W;
+      out_map[pix_id] = M0;
+      out_map[hw + pix_id] = M1;
+      out_map[2 * hw + pix_id] = M2;
+      out_map[3 * hw + pix_id] = M3v;
+    }
+  }
+  uint32_t mc = inside ? last_contributor : 0u;
+  mc = __reduce_max_sync(0xffffffffu, mc);
+  if ((tid & 31) == 0) atomicMax(&s_maxc, mc);
+  __syncthreads();
+  if (tid == 0) tile_maxc[tile] = s_maxc;
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mark_visible_kernel(int64_t P, const float* __restrict__ means3D, const float* __restrict__ vm, uint8_t* __restrict__ present) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= P) return;
+  const float3 v = xform43(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2], vm);
+  present[i] = (v.z <= 0.2f) ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
+                    const float* scales, const float* rotations, const float* cov3D_precomp,
+                    int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st) {
+  GeomState g = GeomState::carve(geom, P, nullptr);
+  const int W = s->image_width, H = s->image_height;
+  const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  const float fy = H / (2.0f * s->tanfovy), fx = W / (2.0f * s->tanfovx);
+  const int64_t nblk = (P + 255) / 256;
+  preprocess_fwd<<<unsigned(nblk), 256, 0, st>>>(P, means3D, opacities, scales, rotations, cov3D_precomp,
+                                                 s->scale_modifier, s->viewmatrix, s->projmatrix, W, H, s->tanfovx,
+                                                 s->tanfovy, fx, fy, gx, gy, s->antialiasing, radii, g);
+  CG_LAUNCH_CHECK(s->debug, st);
+  scan_block_sums<<<1, 1024, 0, st>>>(nblk, g);
+  CG_LAUNCH_CHECK(s->debug, st);
+  uint32_t total = 0;
+  CG_CUDA(cudaMemcpyAsync(&total, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CG_CUDA(cudaStreamSynchronize(st));
+  *num_rendered = int64_t(total);
+  return CG_OK;
+}
+
+int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
+                     void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
+                     float* out_map, cudaStream_t st) {
+  GeomState g = GeomState::carve(geom, P, nullptr);
+  const int W = s->image_width, H = s->image_height;
+  ImgState im = ImgState::carve(img, W, H, nullptr);
+  BinKeep bk = BinKeep::carve(bin_keep, R, nullptr);
+  BinScratch bs = BinScratch::carve(bin_scratch, R, nullptr);
+  const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  const int64_t nblk = (P + 255) / 256;
+  const size_t tiles = size_t(gx) * gy;
+
+  CG_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), st));
+  if (R > 0) {
+    emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, gx, bs.keys[0], bs.vals[0]);
+    CG_LAUNCH_CHECK(s->debug, st);
+    int cur = 0;
+    const int end_bit = 32 + int(tile_key_bits(uint32_t(tiles)));
+    int rc = radix_sort_pairs(bs, R, end_bit, &cur, s->debug != 0, st);
+    if (rc != CG_OK) return rc;
+    const unsigned rb = unsigned((R + 255) / 256);
+    tile_ranges<<<rb, 256, 0, st>>>(R, bs.keys[cur], im.ranges);
+    CG_LAUNCH_CHECK(s->debug, st);
+    gather_records<<<rb, 256, 0, st>>>(R, bs.vals[cur], g, colors, s->render_geo ? all_map : nullptr, bk.rec,
+                                       bk.point_list);
+    CG_LAUNCH_CHECK(s->debug, st);
+  }
+  dim3 grid(gx, gy), block(TILE_X, TILE_Y);
+  if (s->render_geo)
+    blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map, im.final_T,
+                                            im.n_contrib, im.tile_maxc);
+  else
+    blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map, im.final_T,
+                                             im.n_contrib, im.tile_maxc);
+  CG_LAUNCH_CHECK(s->debug, st);
+  return CG_OK;
+}
+
+int launch_mark_visible(int64_t P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t st) {
+  if (P == 0) return CG_OK;
+  mark_visible_kernel<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, means3D, vm, present);
+  CG_LAUNCH_CHECK(0, st);
+  return CG_OK;
+}
+
+}  // namespace cg

@@ -1,0 +1,232 @@
+// Stable LSD radix sort of (uint64 key, uint32 value) pairs, 8 bits per pass,
+// single-pass-per-digit ("onesweep") with decoupled look-back.
+//
+// Replaces cub::DeviceRadixSort::SortPairs in the reference binning step
+// (rasterizer_impl.cu:309-314). The sort must be STABLE: equal (tile, depth)
+// keys keep emission order (ascending Gaussian index), which is what makes
+// point_list bit-exact against the reference.
+//
+// HBM traffic: one 8 B/key histogram pass + per digit pass 12 B read + 12 B
+// write; digit passes whose histogram shows a single occupied bin are still
+// run (ping-pong parity stays fixed), they stream at copy speed.
+#include "common.cuh"
+
+namespace cg {
+
+namespace {
+
+constexpr uint32_t FLAG_SHIFT = 30;
+constexpr uint32_t VALUE_MASK = (1u << FLAG_SHIFT) - 1u;
+constexpr uint32_t FLAG_AGG = 1u;   // tile-local count published
+constexpr uint32_t FLAG_INC = 2u;   // inclusive prefix published
+
+__global__ void __launch_bounds__(256)
+sort_histogram(const uint64_t* __restrict__ keys, int64_t R, int passes, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
+  for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < R; i += stride) {
+    uint64_t k = keys[i];
+    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + ((k >> (8 * p)) & 255u)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
+    uint32_t v = sh[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// One CTA per pass: in-place exclusive scan of that pass's 256 bins.
+__global__ void __launch_bounds__(256) sort_scan_bins(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t wsum[8];
+  uint32_t* h = hist + blockIdx.x * 256;
+  uint32_t v = h[threadIdx.x];
+  uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+  for (uint32_t i = 0; i < w; ++i) base += wsum[i];
+  h[threadIdx.x] = base + inc - v;
+}
+
+struct SortSmem {
+  uint64_t keys[SORT_TILE];
+  uint32_t vals[SORT_TILE];
+  uint32_t whist[SORT_THREADS / 32][257];  // per-warp digit counters (+1 bin for tail padding)
+  uint32_t local_start[256];
+  int32_t gbase[256];                      // global position = gbase[d] + local position
+  uint32_t tile_id;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                   uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                   int64_t R, int shift, const uint32_t* __restrict__ digit_base,
+                   uint32_t* __restrict__ ticket, uint32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortSmem& s = *reinterpret_cast<SortSmem*>(smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int WARPS = SORT_THREADS / 32;
+
+  // Dynamic tile id: a tile only ever waits on tiles that already started.
+  if (tid == 0) s.tile_id = atomicAdd(ticket, 1u);
+  for (int i = tid; i < WARPS * 257; i += SORT_THREADS) (&s.whist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s.tile_id;
+  const int64_t tile_base = int64_t(tile) * SORT_TILE;
+  const int64_t warp_base = tile_base + int64_t(warp) * (32 * SORT_ITEMS);
+
+  uint64_t k[SORT_ITEMS];
+  uint32_t v[SORT_ITEMS];
+  uint16_t rank[SORT_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    int64_t idx = warp_base + i * 32 + lane;
+    bool ok = idx < R;
+    k[i] = ok ? keys_in[idx] : ~0ull;
+    v[i] = ok ? vals_in[idx] : 0u;
+  }
+
+  // Stable in-warp ranking, item by item (items are in memory order).
+  uint32_t* wh = s.whist[warp];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    int64_t idx = warp_base + i * 32 + lane;
+    uint32_t d = (idx < R) ? uint32_t((k[i] >> shift) & 255u) : 256u;
+    uint32_t m = __match_any_sync(0xffffffffu, d);
+    uint32_t leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) {
+      base = wh[d];
+      wh[d] = base + __popc(m);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[i] = uint16_t(base + __popc(m & lt_mask));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // Thread d owns digit d: exclusive scan across warps, tile count, look-back.
+  {
+    const uint32_t d = tid;
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      uint32_t c = s.whist[w][d];
+      s.whist[w][d] = total;
+      total += c;
+    }
+    uint32_t* st = status + size_t(tile) * 256 + d;
+    if (tile == 0) {
+      atomicExch(st, (FLAG_INC << FLAG_SHIFT) | total);
+    } else {
+      atomicExch(st, (FLAG_AGG << FLAG_SHIFT) | total);
+    }
+    // block-wide exclusive scan of `total` over digits -> local_start
+    uint32_t inc = total;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    __shared__ uint32_t wsum[WARPS];
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (uint32_t i = 0; i < warp; ++i) wb += wsum[i];
+    const uint32_t lstart = wb + inc - total;
+    s.local_start[d] = lstart;
+
+    uint32_t excl = 0;
+    if (tile > 0) {
+      int64_t t = int64_t(tile) - 1;
+      while (true) {
+        uint32_t w;
+        volatile uint32_t* p = status + size_t(t) * 256 + d;
+        do { w = *p; } while ((w >> FLAG_SHIFT) == 0u);
+        excl += w & VALUE_MASK;
+        if ((w >> FLAG_SHIFT) == FLAG_INC) break;
+        --t;  // tile 0 always publishes FLAG_INC, so t never goes below 0
+      }
+      atomicExch(st, (FLAG_INC << FLAG_SHIFT) | ((excl + total) & VALUE_MASK));
+    }
+    s.gbase[d] = int32_t(digit_base[d] + excl) - int32_t(lstart);
+  }
+  __syncthreads();
+
+  // Scatter into shared memory at the tile-local sorted position.
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    int64_t idx = warp_base + i * 32 + lane;
+    if (idx < R) {
+      uint32_t d = uint32_t((k[i] >> shift) & 255u);
+      uint32_t pos = s.local_start[d] + s.whist[warp][d] + rank[i];
+      s.keys[pos] = k[i];
+      s.vals[pos] = v[i];
+    }
+  }
+  __syncthreads();
+
+  // Coalesced write-out: consecutive threads write consecutive slots of a digit run.
+  int64_t rem = R - tile_base;
+  const int count = rem < SORT_TILE ? int(rem) : SORT_TILE;
+  for (int j = tid; j < count; j += SORT_THREADS) {
+    uint64_t key = s.keys[j];
+    uint32_t d = uint32_t((key >> shift) & 255u);
+    int64_t g = int64_t(s.gbase[d]) + j;
+    keys_out[g] = key;
+    vals_out[g] = s.vals[j];
+  }
+}
+
+}  // namespace
+
+// Sorts b.keys[0]/b.vals[0] on bits [0,end_bit). *out_buf tells which of the
+// two ping-pong buffers holds the result.
+int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
+                     bool debug, cudaStream_t stream) {
+  *out_buf = 0;
+  if (R <= 0) return CG_OK;
+  if (R >= (int64_t(1) << FLAG_SHIFT)) {
+    set_error("radix sort: %lld instances exceed the 2^30 look-back word", (long long)R);
+    return CG_ERR_CAPACITY;
+  }
+  int passes = (end_bit + 7) / 8;
+  if (passes > SORT_MAX_PASSES) passes = SORT_MAX_PASSES;
+  const int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    CG_CUDA(cudaFuncSetAttribute(sort_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(sizeof(SortSmem))));
+    attr_set = true;
+  }
+  CG_CUDA(cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * SORT_MAX_PASSES * 256, stream));
+  CG_CUDA(cudaMemsetAsync(b.ticket, 0, sizeof(uint32_t) * 32, stream));
+  CG_CUDA(cudaMemsetAsync(b.status, 0, sizeof(uint32_t) * size_t(passes) * ntiles * 256, stream));
+
+  int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  sort_histogram<<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist);
+  CG_LAUNCH_CHECK(debug, stream);
+  sort_scan_bins<<<passes, 256, 0, stream>>>(b.hist);
+  CG_LAUNCH_CHECK(debug, stream);
+
+  int cur = 0;
+  for (int p = 0; p < passes; ++p) {
+    sort_onesweep_pass<<<unsigned(ntiles), SORT_THREADS, sizeof(SortSmem), stream>>>(
+        b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, 8 * p,
+        b.hist + p * 256, b.ticket + p, b.status + size_t(p) * ntiles * 256);
+    CG_LAUNCH_CHECK(debug, stream);
+    cur ^= 1;
+  }
+  *out_buf = cur;
+  return CG_OK;
+}
+
+}  // namespace cg

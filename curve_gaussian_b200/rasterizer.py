@@ -1,0 +1,270 @@
+"""Drop-in for the reference `diff_cur_rasterization` Python module.
+
+Same names, argument order, return values and error behaviour as
+submodules/diff-cur-rasterization/diff_cur_rasterization/__init__.py
+(GaussianRasterizationSettings :153-167, GaussianRasterizer :169-222,
+_RasterizeGaussians :46-151), but every kernel is libcurvegs.so (sm_100a)
+called through the C ABI; torch only owns memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool
+    render_geo: bool
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _settings_struct(rs: GaussianRasterizationSettings, keep: list) -> _lib.RasterSettings:
+    bg = _f32c(rs.bg)
+    vm = _f32c(rs.viewmatrix)
+    pm = _f32c(rs.projmatrix)
+    keep.extend([bg, vm, pm])
+    for name, t in (("bg", bg), ("viewmatrix", vm), ("projmatrix", pm)):
+        if not t.is_cuda:
+            raise _lib.CurveGSError(f"raster_settings.{name} must be a CUDA tensor")
+    s = _lib.RasterSettings()
+    s.image_height = int(rs.image_height)
+    s.image_width = int(rs.image_width)
+    s.tanfovx = float(rs.tanfovx)
+    s.tanfovy = float(rs.tanfovy)
+    s.scale_modifier = float(rs.scale_modifier)
+    s.render_geo = int(bool(rs.render_geo))
+    s.debug = int(bool(rs.debug))
+    s.antialiasing = int(bool(rs.antialiasing))
+    s.bg = bg.data_ptr()
+    s.viewmatrix = vm.data_ptr()
+    s.projmatrix = pm.data_ptr()
+    return s
+
+
+def _bytes(n: int, device) -> torch.Tensor:
+    # torch's caching allocator returns 512-byte aligned blocks
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, all_maps):
+    """The `_C.rasterize_gaussians` equivalent (rasterize_points.cu:35-130).
+
+    Returns (num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer, invdepths, out_all_map).
+    """
+    lib = _lib.load()
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    dev = means3D.device
+    if not means3D.is_cuda:
+        raise _lib.CurveGSError("means3D must be a CUDA tensor; there is no CPU path")
+    P = means3D.shape[0]
+    H, W = int(rs.image_height), int(rs.image_width)
+    if P == 0:
+        # reference: forward is skipped and the zero-filled outputs are returned (rasterize_points.cu:71-91)
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        e = torch.empty(0, dtype=torch.uint8, device=dev)
+        return 0, z(1, H, W), torch.zeros(0, dtype=torch.int32, device=dev), e, e, e, z(1, H, W), z(4, H, W)
+    keep: list = []
+    s = _settings_struct(rs, keep)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    color = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+    invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+    out_all_map = torch.zeros((4, H, W), dtype=torch.float32, device=dev) if not rs.render_geo else \
+        torch.empty((4, H, W), dtype=torch.float32, device=dev)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    geom = _bytes(lib.cg_raster_geom_bytes(P), dev)
+    img = _bytes(lib.cg_raster_img_bytes(W, H), dev)
+
+    means3D = _f32c(means3D)
+    opacities = _f32c(opacities)
+    scales = _f32c(scales) if scales is not None and scales.numel() else None
+    rotations = _f32c(rotations) if rotations is not None and rotations.numel() else None
+    cov3D = _f32c(cov3Ds_precomp) if cov3Ds_precomp is not None and cov3Ds_precomp.numel() else None
+    colors = _f32c(colors_precomp) if colors_precomp is not None and colors_precomp.numel() else None
+    amap = _f32c(all_maps) if all_maps is not None and all_maps.numel() else None
+    if P > 0 and colors is None:
+        raise _lib.CurveGSError("colors_precomp is required (the SH path is not part of the curve pipeline)")
+
+    R = C.c_int64(0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.cg_raster_fwd_geom(C.byref(s), P, _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales),
+                                          _lib.ptr(rotations), _lib.ptr(cov3D), _lib.ptr(radii), geom.data_ptr(),
+                                          geom.numel(), C.byref(R), stream), "cg_raster_fwd_geom")
+        R = int(R.value)
+        bin_keep = _bytes(lib.cg_raster_bin_keep_bytes(R), dev)
+        bin_scratch = _bytes(lib.cg_raster_bin_scratch_bytes(R), dev)
+        _lib.check(lib.cg_raster_fwd_blend(C.byref(s), P, R, _lib.ptr(colors), _lib.ptr(amap), geom.data_ptr(),
+                                           img.data_ptr(), bin_keep.data_ptr(), bin_scratch.data_ptr(),
+                                           color.data_ptr(), invdepth.data_ptr(), out_all_map.data_ptr(), stream),
+                   "cg_raster_fwd_blend")
+    # keep scratch reachable for debug_fetch of the sorted keys
+    rasterize_forward_raw.last_scratch = bin_scratch
+    return R, color, radii, geom, bin_keep, img, invdepth, out_all_map
+
+
+def rasterize_backward_raw(rs, means3D, radii, colors_precomp, all_maps, opacities, scales, rotations,
+                           cov3Ds_precomp, grad_color, grad_invdepth, grad_all_map, geom, R, bin_keep, img):
+    """The `_C.rasterize_gaussians_backward` equivalent (rasterize_points.cu:133-240).
+
+    Returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+    dL_drotations, dL_dall_map).
+    """
+    lib = _lib.load()
+    dev = means3D.device
+    P = means3D.shape[0]
+    f = dict(dtype=torch.float32, device=dev)
+    if P == 0:
+        z = lambda *shape: torch.zeros(shape, **f)
+        return z(0, 3), z(0, 1), z(0, 1), z(0, 3), z(0, 6), z(0, 0, 3), z(0, 3), z(0, 4), z(0, 4)
+    keep: list = []
+    s = _settings_struct(rs, keep)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    d_means2D = torch.empty((P, 3), **f)
+    d_colors = torch.empty((P, 1), **f)
+    d_opacity = torch.empty((P, 1), **f)
+    d_means3D = torch.empty((P, 3), **f)
+    d_cov3D = torch.empty((P, 6), **f)
+    d_sh = torch.zeros((P, 0, 3), **f)
+    d_scales = torch.empty((P, 3), **f)
+    d_rot = torch.empty((P, 4), **f)
+    d_all_map = torch.empty((P, 4), **f)
+    scratch = _bytes(lib.cg_raster_bwd_scratch_bytes(P), dev)
+
+    means3D = _f32c(means3D)
+    opacities = _f32c(opacities)
+    scales = _f32c(scales) if scales is not None and scales.numel() else None
+    rotations = _f32c(rotations) if rotations is not None and rotations.numel() else None
+    cov3D = _f32c(cov3Ds_precomp) if cov3Ds_precomp is not None and cov3Ds_precomp.numel() else None
+    if cov3D is not None:
+        d_scales.zero_()
+        d_rot.zero_()
+    g_color = _f32c(grad_color)
+    g_invd = _f32c(grad_invdepth) if grad_invdepth is not None and grad_invdepth.numel() else None
+    g_map = _f32c(grad_all_map) if grad_all_map is not None and grad_all_map.numel() else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.cg_raster_bwd(C.byref(s), P, int(R), _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales),
+                                     _lib.ptr(rotations), _lib.ptr(cov3D), _lib.ptr(radii), geom.data_ptr(),
+                                     img.data_ptr(), bin_keep.data_ptr(), g_color.data_ptr(), _lib.ptr(g_invd),
+                                     _lib.ptr(g_map), scratch.data_ptr(), d_means2D.data_ptr(), d_colors.data_ptr(),
+                                     d_opacity.data_ptr(), d_means3D.data_ptr(), d_cov3D.data_ptr(),
+                                     d_scales.data_ptr(), d_rot.data_ptr(), d_all_map.data_ptr(), stream),
+                   "cg_raster_bwd")
+    return d_means2D, d_colors, d_opacity, d_means3D, d_cov3D, d_sh, d_scales, d_rot, d_all_map
+
+
+def mark_visible(positions, viewmatrix, projmatrix):
+    lib = _lib.load()
+    P = positions.shape[0]
+    present = torch.zeros((P,), dtype=torch.bool, device=positions.device)
+    if P:
+        positions = _f32c(positions)
+        vm, pm = _f32c(viewmatrix), _f32c(projmatrix)
+        with torch.cuda.device(positions.device):
+            _lib.check(lib.cg_mark_visible(P, positions.data_ptr(), vm.data_ptr(), pm.data_ptr(), present.data_ptr(),
+                                           torch.cuda.current_stream(positions.device).cuda_stream), "cg_mark_visible")
+    return present
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, all_map,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, all_map, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, all_maps,
+                raster_settings):
+        if sh is not None and sh.numel() != 0:
+            raise _lib.CurveGSError("SH colours are not part of the curve-Gaussian hot path; pass colors_precomp")
+        (num_rendered, color, radii, geom, bin_keep, img, invdepths, out_all_map) = rasterize_forward_raw(
+            raster_settings, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, all_maps)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        # unused outputs then arrive as None instead of materialised zero images; the
+        # kernels skip those channels, which is bit-identical to adding zeros
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii)
+        ctx.save_for_backward(colors_precomp, all_maps, means3D, scales, rotations, cov3Ds_precomp, radii, opacities,
+                              geom, bin_keep, img)
+        return color, radii, invdepths, out_all_map
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_all_map):
+        rs = ctx.raster_settings
+        (colors_precomp, all_maps, means3D, scales, rotations, cov3Ds_precomp, radii, opacities, geom, bin_keep,
+         img) = ctx.saved_tensors
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((1, rs.image_height, rs.image_width), dtype=torch.float32,
+                                         device=means3D.device)
+        (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_all_map) = rasterize_backward_raw(
+            rs, means3D, radii, colors_precomp, all_maps, opacities, scales, rotations, cov3Ds_precomp,
+            grad_out_color, grad_out_depth, grad_out_all_map, geom, ctx.num_rendered, bin_keep, img)
+        if opacities.dim() == 1:
+            g_opac = g_opac.view(-1)
+
+        def like(g, t):
+            if t is None or t.numel() == 0:
+                return None
+            return g.view(t.shape) if g.numel() == t.numel() else g
+
+        return (g_means3D, g_means2D, None, like(g_colors, colors_precomp), g_opac, like(g_scales, scales),
+                like(g_rot, rotations), like(g_cov3D, cov3Ds_precomp), like(g_all_map, all_maps), None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, all_map=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        empty = torch.Tensor([])
+        if shs is None:
+            shs = empty
+        if colors_precomp is None:
+            colors_precomp = empty
+        if scales is None:
+            scales = empty
+        if rotations is None:
+            rotations = empty
+        if cov3D_precomp is None:
+            cov3D_precomp = empty
+        if all_map is None:
+            all_map = empty
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, all_map, rs)

@@ -1,0 +1,186 @@
+/*
+ * curvegs.h — C ABI of libcurvegs.so, the B200 (sm_100a) curve-Gaussian hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + a CUDA stream handle
+ * (cudaStream_t passed as void*), owns no memory, never throws, and returns
+ * 0 on success or a negative CG_ERR_* code (cg_last_error() gives the text).
+ * The caller (PyTorch host code, or any FFI) allocates all outputs and the
+ * opaque state buffers, exactly as the reference's pybind layer hands
+ * torch-owned byte tensors to CudaRasterizer through resize callbacks
+ * (reference: submodules/diff-cur-rasterization/rasterize_points.cu:27-33,
+ * cuda_rasterizer/rasterizer.h:24-98).
+ *
+ * Reference interfaces replaced (file:line under the reference checkout):
+ *   cg_raster_*        -> _C.rasterize_gaussians / _C.rasterize_gaussians_backward
+ *                         (rasterize_points.cu:35-130, :133-240; rasterizer_impl.cu:198-466)
+ *   cg_mark_visible    -> _C.mark_visible (rasterize_points.cu:242-260)
+ *   cg_sample_*        -> GaussianCurveModel.prepare_scaling_rot + rot_to_quat_batch
+ *                         (scene/gaussian_curve_model.py:70-89,180-198; utils/general_utils.py:9-86)
+ *   cg_ssim_*          -> fused_ssim_cuda.fusedssim / fusedssim_backward (fused-ssim/ssim.cu:368-444)
+ *   cg_knn_mean_dist2  -> simple_knn._C.distCUDA2 (simple-knn/spatial.cu:15-26, simple_knn.cu:186-222)
+ *
+ * All float tensors are fp32, contiguous row-major; "absent" tensors are NULL.
+ */
+#ifndef CURVEGS_H_
+#define CURVEGS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_OK 0
+#define CG_ERR_ARG (-1)      /* bad argument (null / shape / alignment) */
+#define CG_ERR_CUDA (-2)     /* a CUDA runtime call or launch failed */
+#define CG_ERR_CAPACITY (-3) /* a caller-provided buffer is too small */
+
+/* ABI version, bumped on any signature change. */
+int cg_abi_version(void);
+/* Thread-local text of the last error returned on this thread. */
+const char* cg_last_error(void);
+
+/* ------------------------------------------------------------------ */
+/* Rasterizer (reference: diff_cur_rasterization._C)                   */
+/* ------------------------------------------------------------------ */
+
+/* Camera / raster settings; mirrors GaussianRasterizationSettings
+ * (diff_cur_rasterization/__init__.py:153-167). Matrices are DEVICE pointers
+ * to 16 floats, row-major torch layout used with row vectors
+ * (auxiliary.h:70-89). bg is a DEVICE pointer; only bg[0] is read
+ * (NUM_CHANNELS == 1, config.h:15). */
+typedef struct cg_raster_settings {
+  int32_t image_height;
+  int32_t image_width;
+  float tanfovx;
+  float tanfovy;
+  float scale_modifier;
+  int32_t render_geo;   /* blend the 4 all_map channels (config.h NUM_ALL_MAP) */
+  int32_t debug;        /* synchronize + check after every stage (auxiliary.h:178-185) */
+  int32_t antialiasing; /* opacity compensation for the 0.3 px dilation (forward.cu:219-227) */
+  const float* bg;
+  const float* viewmatrix;
+  const float* projmatrix;
+} cg_raster_settings;
+
+/* Sizes of the opaque state buffers the caller must allocate (bytes).
+ * geom: per-Gaussian state, img: per-pixel/per-tile state, both saved for
+ * backward. bin_keep: sorted per-instance records + point list, saved for
+ * backward. bin_scratch: sort double buffers, only live during forward. */
+size_t cg_raster_geom_bytes(int64_t P);
+size_t cg_raster_img_bytes(int32_t W, int32_t H);
+size_t cg_raster_bin_keep_bytes(int64_t R);
+size_t cg_raster_bin_scratch_bytes(int64_t R);
+
+/* Forward, stage 1: per-Gaussian EWA projection + tile counts + prefix scan.
+ * Writes radii[P] (int32) and the geom state; returns the number of
+ * tile-instances R through *num_rendered (host int; this call synchronizes
+ * the stream for that 4-byte read, as rasterizer_impl.cu:287 does).
+ * Exactly one of (scales+rotations) / cov3D_precomp must be non-NULL. */
+int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P,
+                       const float* means3D,      /* (P,3) */
+                       const float* opacities,    /* (P) */
+                       const float* scales,       /* (P,3) or NULL */
+                       const float* rotations,    /* (P,4) raw quaternion, or NULL */
+                       const float* cov3D_precomp,/* (P,6) or NULL */
+                       int32_t* radii,            /* out (P) */
+                       void* geom, size_t geom_bytes,
+                       int64_t* num_rendered,     /* out, host */
+                       void* stream);
+
+/* Forward, stage 2: duplicate -> stable radix sort -> tile ranges -> record
+ * gather -> per-tile front-to-back blend. colors is (P,1); all_map is (P,4)
+ * or NULL when !render_geo. Outputs are (1,H,W), (1,H,W), (4,H,W). */
+int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R,
+                        const float* colors, const float* all_map,
+                        void* geom, void* img,
+                        void* bin_keep, void* bin_scratch,
+                        float* out_color, float* out_invdepth, float* out_all_map,
+                        void* stream);
+
+/* Backward. dL_dinvdepth / dL_dall_map may be NULL (treated as zeros, which is
+ * what autograd materialises for unused outputs). Gradient outputs follow
+ * rasterize_points.cu:173-193: dL_dmeans2D (P,3), dL_dcolors (P,1),
+ * dL_dopacity (P,1), dL_dmeans3D (P,3), dL_dcov3D (P,6), dL_dscales (P,3),
+ * dL_drotations (P,4), dL_dall_map (P,4). The caller need not zero them.
+ * grad_scratch must hold cg_raster_bwd_scratch_bytes(P). */
+size_t cg_raster_bwd_scratch_bytes(int64_t P);
+int cg_raster_bwd(const cg_raster_settings* s, int64_t P, int64_t R,
+                  const float* means3D, const float* opacities, const float* scales,
+                  const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                  const void* geom, const void* img, const void* bin_keep,
+                  const float* dL_dcolor, const float* dL_dinvdepth, const float* dL_dall_map,
+                  void* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* dL_dall_map_in,
+                  void* stream);
+
+/* present[i] = (view-space z > 0.2)  (rasterizer_impl.cu:54-66). */
+int cg_mark_visible(int64_t P, const float* means3D, const float* viewmatrix,
+                    const float* projmatrix, uint8_t* present, void* stream);
+
+/* Introspection for parity tests: copies of internal state as typed arrays.
+ * which: 0 = sorted keys (uint64, R)   1 = sorted point list (uint32, R)
+ *        2 = tile ranges (uint32 pairs, tiles)  3 = tiles_touched (uint32, P)
+ *        4 = means2D (float2, P)  5 = depths (float, P)  6 = conic_opacity (float4, P)
+ *        7 = n_contrib (uint32, W*H)  8 = final_T (float, W*H)
+ * Keys (0) are only valid between cg_raster_fwd_blend and the next call that
+ * reuses bin_scratch. dst is a DEVICE pointer with room for the array. */
+int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
+                          const void* geom, const void* img, const void* bin_keep,
+                          const void* bin_scratch, void* dst, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Curve -> Gaussian sampling (reference: scene/gaussian_curve_model.py)*/
+/* ------------------------------------------------------------------ */
+
+/* Forward of prepare_scaling_rot (:180-198). curve_points (B,4,3), width (B),
+ * is_bezier (B) bytes, t (n) sample parameters (torch.linspace values, :58-60),
+ * half_step = 0.5/n. Outputs, Gaussian index g = b*n + m:
+ *   xyz (P,3), rotation (P,4) un-normalised w>=0 quaternion, scaling (P,3).
+ * norms (2 floats, device) receives the two whole-tensor Frobenius norms
+ * (:190,:192) and must be kept for the backward. */
+size_t cg_sample_scratch_bytes(int64_t B, int32_t n);
+int cg_sample_fwd(int64_t B, int32_t n, const float* curve_points, const float* width,
+                  const uint8_t* is_bezier, const float* t, float half_step,
+                  float* xyz, float* rotation, float* scaling,
+                  float* norms, void* scratch, void* stream);
+
+/* Adjoint: (dL_dxyz, dL_drotation, dL_dscaling) -> dL_dcurve_points (B,4,3),
+ * dL_dwidth (B). Any of the three upstream grads may be NULL (zeros). */
+int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* width,
+                  const uint8_t* is_bezier, const float* t, float half_step,
+                  const float* norms,
+                  const float* dL_dxyz, const float* dL_drotation, const float* dL_dscaling,
+                  float* dL_dcurve_points, float* dL_dwidth,
+                  void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Fused SSIM (reference: submodules/fused-ssim)                        */
+/* ------------------------------------------------------------------ */
+
+/* img1/img2 (B,CH,H,W). ssim_map always written; the three partial maps only
+ * when non-NULL (train=True). */
+int cg_ssim_fwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                const float* img1, const float* img2, float* ssim_map,
+                float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* stream);
+int cg_ssim_bwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                const float* img1, const float* img2, const float* dL_dmap,
+                const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
+                float* dL_dimg1, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* simple-knn (reference: submodules/simple-knn)                        */
+/* ------------------------------------------------------------------ */
+
+/* mean_dist2[i] = mean of the 3 smallest squared distances to other points. */
+size_t cg_knn_scratch_bytes(int64_t P);
+int cg_knn_mean_dist2(int64_t P, const float* points, float* mean_dist2,
+                      void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURVEGS_H_ */
