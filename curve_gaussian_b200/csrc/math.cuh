@@ -1,10 +1,17 @@
 // Small fp32 matrix helpers used by the EWA projection kernels.
 //
-// Bit-exact parity with the reference needs the same fp32 expression trees the
-// reference gets from glm (column-major mat3, product written as
-// a0*b0 + a1*b1 + a2*b2 per element) so that nvcc's FMA contraction lands on
-// the same operations. M3 stores m[col][row] like glm::mat3 and mul() sums in
-// glm's k = 0,1,2 order (third_party/glm/glm/detail/type_mat3x3.inl, operator*).
+// Bit-exact tile/sort keys need every fp32 operation of the projection to round
+// exactly like the reference build does. The reference leaves FMA contraction
+// to the compiler (glm column-major mat3 products a0*b0 + a1*b1 + a2*b2, plain
+// C expressions elsewhere); which pairs get fused there was read off its
+// sm_100 SASS (oracle/_ref, nvcc 12.9) and is PINNED here with explicit
+// __fmaf_rn/__fmul_rn/__fadd_rn intrinsics, which no compiler pass may re-fuse
+// or split. Patterns:
+//   3-term products   fma(a2,b2, fma(a0,b0, rn(a1*b1)))
+//   affine transform  fma(z,m8, fma(x,m0, rn(y*m4))) + m12      (plain add last)
+//   x*y -/+ r*z       fma(x,y, -/+ rn(r*z));   x*z +/- r*y = fma(+/-r,y, rn(x*z))
+//   a*c - b*b         fma(a,c, -rn(b*b))
+// M3 stores m[col][row] like glm::mat3 (type_mat3x3.inl).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -24,13 +31,17 @@ __device__ __forceinline__ M3 m3_cols(float c00, float c01, float c02,
   return r;
 }
 
+__device__ __forceinline__ float dot3p(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
+
 __device__ __forceinline__ M3 m3_mul(const M3& a, const M3& b) {
   M3 r;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int rw = 0; rw < 3; ++rw)
-      r.m[c][rw] = a.m[0][rw] * b.m[c][0] + a.m[1][rw] * b.m[c][1] + a.m[2][rw] * b.m[c][2];
+      r.m[c][rw] = dot3p(a.m[0][rw], b.m[c][0], a.m[1][rw], b.m[c][1], a.m[2][rw], b.m[c][2]);
   return r;
 }
 
@@ -46,34 +57,44 @@ __device__ __forceinline__ M3 m3_t(const M3& a) {
 // [x y z 1] @ M, M read as m[4*i + j] (auxiliary.h:70-89).
 __device__ __forceinline__ float3 xform43(float x, float y, float z, const float* m) {
   float3 r;
-  r.x = m[0] * x + m[4] * y + m[8] * z + m[12];
-  r.y = m[1] * x + m[5] * y + m[9] * z + m[13];
-  r.z = m[2] * x + m[6] * y + m[10] * z + m[14];
+  r.x = __fadd_rn(dot3p(m[0], x, m[4], y, m[8], z), m[12]);
+  r.y = __fadd_rn(dot3p(m[1], x, m[5], y, m[9], z), m[13]);
+  r.z = __fadd_rn(dot3p(m[2], x, m[6], y, m[10], z), m[14]);
   return r;
 }
 __device__ __forceinline__ float4 xform44(float x, float y, float z, const float* m) {
   float4 r;
-  r.x = m[0] * x + m[4] * y + m[8] * z + m[12];
-  r.y = m[1] * x + m[5] * y + m[9] * z + m[13];
-  r.z = m[2] * x + m[6] * y + m[10] * z + m[14];
-  r.w = m[3] * x + m[7] * y + m[11] * z + m[15];
+  r.x = __fadd_rn(dot3p(m[0], x, m[4], y, m[8], z), m[12]);
+  r.y = __fadd_rn(dot3p(m[1], x, m[5], y, m[9], z), m[13]);
+  r.z = __fadd_rn(dot3p(m[2], x, m[6], y, m[10], z), m[14]);
+  r.w = __fadd_rn(dot3p(m[3], x, m[7], y, m[11], z), m[15]);
   return r;
 }
 
 // Rotation matrix of a RAW (not normalised) real-first quaternion, glm column
 // layout as in forward.cu:118-152 / backward.cu:329-392.
 __device__ __forceinline__ M3 quat_to_m3(float r, float x, float y, float z) {
-  return m3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                 2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                 2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+  const float rz = __fmul_rn(r, z), rx = __fmul_rn(r, x), xz = __fmul_rn(x, z);
+  const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+  const float xy_m = __fmaf_rn(x, y, -rz), xy_p = __fmaf_rn(x, y, rz);
+  const float xz_p = __fmaf_rn(r, y, xz), xz_m = __fmaf_rn(-r, y, xz);
+  const float yz_m = __fmaf_rn(y, z, -rx), yz_p = __fmaf_rn(y, z, rx);
+  const float yy_zz = __fadd_rn(yy, zz), xx_zz = __fmaf_rn(x, x, zz), xx_yy = __fmaf_rn(x, x, yy);
+  return m3_cols(__fsub_rn(1.f, __fadd_rn(yy_zz, yy_zz)), __fadd_rn(xy_m, xy_m), __fadd_rn(xz_p, xz_p),
+                 __fadd_rn(xy_p, xy_p), __fsub_rn(1.f, __fadd_rn(xx_zz, xx_zz)), __fadd_rn(yz_m, yz_m),
+                 __fadd_rn(xz_m, xz_m), __fadd_rn(yz_p, yz_p), __fsub_rn(1.f, __fadd_rn(xx_yy, xx_yy)));
 }
 
 // Sigma = (S R)^T (S R), upper triangle [xx,xy,xz,yy,yz,zz] (forward.cu:118-152).
 __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float sz, float mod,
                                                      float4 q, float* cov6) {
-  M3 S = m3_cols(mod * sx, 0.f, 0.f, 0.f, mod * sy, 0.f, 0.f, 0.f, mod * sz);
+  const float s[3] = {__fmul_rn(mod, sx), __fmul_rn(mod, sy), __fmul_rn(mod, sz)};
   M3 R = quat_to_m3(q.x, q.y, q.z, q.w);
-  M3 M = m3_mul(S, R);
+  M3 M;  // S*R with S diagonal: every entry is the single rounded product s_row * R
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int rw = 0; rw < 3; ++rw) M.m[c][rw] = __fmul_rn(s[rw], R.m[c][rw]);
   M3 Sg = m3_mul(m3_t(M), M);
   cov6[0] = Sg.m[0][0]; cov6[1] = Sg.m[0][1]; cov6[2] = Sg.m[0][2];
   cov6[3] = Sg.m[1][1]; cov6[4] = Sg.m[1][2]; cov6[5] = Sg.m[2][2];
@@ -93,15 +114,16 @@ __device__ __forceinline__ Proj2D project_cov(float x, float y, float z, float f
                                               const float* vm) {
   Proj2D p;
   float3 t = xform43(x, y, z, vm);
-  const float limx = 1.3f * tanx;
-  const float limy = 1.3f * tany;
-  p.txtz = t.x / t.z;
-  p.tytz = t.y / t.z;
-  t.x = fminf(limx, fmaxf(-limx, p.txtz)) * t.z;
-  t.y = fminf(limy, fmaxf(-limy, p.tytz)) * t.z;
+  const float limx = __fmul_rn(1.3f, tanx);
+  const float limy = __fmul_rn(1.3f, tany);
+  p.txtz = __fdiv_rn(t.x, t.z);
+  p.tytz = __fdiv_rn(t.y, t.z);
+  t.x = __fmul_rn(fminf(limx, fmaxf(-limx, p.txtz)), t.z);
+  t.y = __fmul_rn(fminf(limy, fmaxf(-limy, p.tytz)), t.z);
   p.t = t;
-  M3 J = m3_cols(fx / t.z, 0.0f, -(fx * t.x) / (t.z * t.z),
-                 0.0f, fy / t.z, -(fy * t.y) / (t.z * t.z),
+  const float tz2 = __fmul_rn(t.z, t.z);
+  M3 J = m3_cols(__fdiv_rn(fx, t.z), 0.0f, __fdiv_rn(-__fmul_rn(fx, t.x), tz2),
+                 0.0f, __fdiv_rn(fy, t.z), __fdiv_rn(-__fmul_rn(fy, t.y), tz2),
                  0.f, 0.f, 0.f);
   M3 Wm = m3_cols(vm[0], vm[4], vm[8], vm[1], vm[5], vm[9], vm[2], vm[6], vm[10]);
   p.T = m3_mul(Wm, J);

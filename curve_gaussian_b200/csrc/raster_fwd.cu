@@ -28,7 +28,7 @@ __device__ __forceinline__ void stage_floats(const float* __restrict__ src, floa
 
 __device__ __forceinline__ float ndc_to_pix(float v, int S) {
   // double arithmetic on purpose: the reference's literals are doubles (auxiliary.h:40-43)
-  return float(((double(v) + 1.0) * double(S) - 1.0) * 0.5);
+  return float(__dmul_rn(__fma_rn(__dadd_rn(double(v), 1.0), double(S), -1.0), 0.5));
 }
 
 __global__ void __launch_bounds__(256)
@@ -59,8 +59,8 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
     const float3 p_view = xform43(px, py, pz, s_vm);
     if (!(p_view.z <= 0.2f)) {  // near cull only, no x/y frustum test (auxiliary.h:166)
       const float4 p_hom = xform44(px, py, pz, s_pm);
-      const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-      const float ndc_x = p_hom.x * p_w, ndc_y = p_hom.y * p_w;
+      const float p_w = __frcp_rn(__fadd_rn(p_hom.w, 0.0000001f));
+      const float ndc_x = __fmul_rn(p_hom.x, p_w), ndc_y = __fmul_rn(p_hom.y, p_w);
 
       float cov6[6];
       if (cov3D_precomp) {
@@ -76,19 +76,22 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
       Proj2D pr = project_cov(px, py, pz, fx, fy, tanx, tany, cov6, s_vm);
       float3 cov = pr.cov;
       constexpr float h_var = 0.3f;
-      const float det_cov = cov.x * cov.z - cov.y * cov.y;
-      cov.x += h_var;
-      cov.z += h_var;
-      const float det = cov.x * cov.z - cov.y * cov.y;
+      // a*c - b*b with one shared rounded b*b (see math.cuh on pinned contraction)
+      const float bb = __fmul_rn(cov.y, cov.y);
+      const float det_cov = __fmaf_rn(cov.x, cov.z, -bb);
+      cov.x = __fadd_rn(cov.x, h_var);
+      cov.z = __fadd_rn(cov.z, h_var);
+      const float det = __fmaf_rn(cov.x, cov.z, -bb);
       float h_scaling = 1.0f;
-      if (antialiasing) h_scaling = sqrtf(fmaxf(0.000025f, det_cov / det));
+      if (antialiasing) h_scaling = sqrtf(fmaxf(0.000025f, __fdiv_rn(det_cov, det)));
       if (det != 0.0f) {
-        const float det_inv = 1.f / det;
-        const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
-        const float mid = 0.5f * (cov.x + cov.z);
-        const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-        const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-        const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+        const float det_inv = __frcp_rn(det);
+        const float3 conic = make_float3(__fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv));
+        const float mid = __fmul_rn(__fadd_rn(cov.x, cov.z), 0.5f);
+        const float disc = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+        const float lambda1 = __fadd_rn(mid, disc);
+        const float lambda2 = __fsub_rn(mid, disc);
+        const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.f));
         const float pix_x = ndc_to_pix(ndc_x, W), pix_y = ndc_to_pix(ndc_y, H);
         const int rad = int(my_radius);
         // tile rectangle (auxiliary.h:45-55); int() truncates toward zero
