@@ -173,16 +173,3 @@ int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
 }
 
 }  // extern "C"
-
-// ---- TEMPORARY stubs until sample.cu / ssim.cu / knn.cu land (removed in the same round) ----
-#ifndef CG_HAVE_SAMPLE
-extern "C" {
-size_t cg_sample_scratch_bytes(int64_t, int32_t) { return 0; }
-int cg_sample_fwd(int64_t, int32_t, const float*, const float*, const uint8_t*, const float*, float, float*, float*, float*, float*, void*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
-int cg_sample_bwd(int64_t, int32_t, const float*, const float*, const uint8_t*, const float*, float, const float*, const float*, const float*, const float*, float*, float*, void*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
-int cg_ssim_fwd(int32_t, int32_t, int32_t, int32_t, float, float, const float*, const float*, float*, float*, float*, float*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
-int cg_ssim_bwd(int32_t, int32_t, int32_t, int32_t, float, float, const float*, const float*, const float*, const float*, const float*, const float*, float*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
-size_t cg_knn_scratch_bytes(int64_t) { return 0; }
-int cg_knn_mean_dist2(int64_t, const float*, float*, void*, void*) { cg::set_error("not built"); return CG_ERR_ARG; }
-}
-#endif

@@ -100,6 +100,14 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
   cov6[3] = Sg.m[1][1]; cov6[4] = Sg.m[1][2]; cov6[5] = Sg.m[2][2];
 }
 
+// Exponent of the 2D Gaussian, -0.5*(A dx^2 + C dy^2) - B dx dy, with the
+// reference build's rounding: fma(fma(dx, rn(A dx), rn(rn(C dy) dy)), -0.5, -rn(rn(B dx) dy))
+// (forward.cu:356, backward.cu:563).
+__device__ __forceinline__ float gauss_power(float A, float B, float C, float dx, float dy) {
+  const float inner = __fmaf_rn(dx, __fmul_rn(A, dx), __fmul_rn(__fmul_rn(C, dy), dy));
+  return __fmaf_rn(inner, -0.5f, -__fmul_rn(__fmul_rn(B, dx), dy));
+}
+
 struct Proj2D {
   float3 t;       // clamped view-space point
   float txtz, tytz;

@@ -317,22 +317,22 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, 
       contributor++;
       const float4 a = *reinterpret_cast<const float4*>(&batch[j].x);    // x y ca cb
       const float2 c2 = *reinterpret_cast<const float2*>(&batch[j].cc);  // cc o
-      const float dx = a.x - pxf, dy = a.y - pyf;
-      const float power = -0.5f * (a.z * dx * dx + c2.x * dy * dy) - a.w * dx * dy;
+      const float dx = __fsub_rn(a.x, pxf), dy = __fsub_rn(a.y, pyf);
+      const float power = gauss_power(a.z, a.w, c2.x, dx, dy);
       if (power > 0.0f) continue;
-      const float alpha = fminf(0.99f, c2.y * expf(power));
+      const float alpha = fminf(0.99f, __fmul_rn(c2.y, expf(power)));
       if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = T * (1 - alpha);
+      const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
       if (test_T < 0.0001f) { done = true; continue; }
       const float2 ci = *reinterpret_cast<const float2*>(&batch[j].col);  // col invd
-      C += ci.x * alpha * T;
-      invd_acc += ci.y * alpha * T;
+      C = __fmaf_rn(__fmul_rn(ci.x, alpha), T, C);
+      invd_acc = __fmaf_rn(__fmul_rn(ci.y, alpha), T, invd_acc);
       if (GEO) {
         const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
-        M0 += mp.x * alpha * T;
-        M1 += mp.y * alpha * T;
-        M2 += mp.z * alpha * T;
-        M3v += mp.w * alpha * T;
+        M0 = __fmaf_rn(__fmul_rn(mp.x, alpha), T, M0);
+        M1 = __fmaf_rn(__fmul_rn(mp.y, alpha), T, M1);
+        M2 = __fmaf_rn(__fmul_rn(mp.z, alpha), T, M2);
+        M3v = __fmaf_rn(__fmul_rn(mp.w, alpha), T, M3v);
       }
       T = test_T;
       last_contributor = contributor;
@@ -342,7 +342,7 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, 
   if (inside) {
     final_T[pix_id] = T;
     n_contrib[pix_id] = last_contributor;
-    out_color[pix_id] = C + T * bg[0];
+    out_color[pix_id] = __fmaf_rn(T, bg[0], C);
     out_invd[pix_id] = invd_acc;
     if (GEO) {
       const size_t hw = size_t(H) * W;

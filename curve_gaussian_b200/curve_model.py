@@ -1,0 +1,137 @@
+"""Host-side mirror of the reference GaussianCurveModel's hot-path surface
+(scene/gaussian_curve_model.py:54-198): same attribute names, properties and
+`prepare_scaling_rot()`, with the sampling math running as the fused CUDA op in
+sampling.py. Topology surgery, optimizer bookkeeping and ply I/O (the rest of that
+727-line class) are host control logic outside the hot path and are
+not reimplemented; they only need `prepare_scaling_rot()` to keep working after
+they edit `_curve_points/_width/_opacity/_mask/is_bezier`, which it does.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import sampling
+from .knn import distCUDA2
+
+
+def quaternion_to_matrix(quaternions: torch.Tensor) -> torch.Tensor:
+    """Real-first quaternion -> rotation matrix (pytorch3d.transforms formula; the reference
+    imports it at scene/gaussian_curve_model.py:6 and calls it at :97)."""
+    r, i, j, k = torch.unbind(quaternions, -1)
+    two_s = 2.0 / (quaternions * quaternions).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(quaternions.shape[:-1] + (3, 3))
+
+
+def initialize_bezier_curves(points, bound, n_control_points=4):
+    """One vertical cubic Bezier per point (scene/gaussian_curve_model.py:27-51)."""
+    assert n_control_points == 4
+    direction = torch.cat([torch.zeros_like(bound), bound, torch.zeros_like(bound)], dim=1)
+    return torch.stack([points - direction, points - 0.5 * direction, points + 0.5 * direction, points + direction],
+                       dim=1)
+
+
+class GaussianCurveModel:
+    def __init__(self, sh_degree=0, n_gaussians=12, optimizer_type="default", device="cuda"):
+        self.active_sh_degree = 0
+        self.max_sh_degree = sh_degree
+        self.optimizer_type = optimizer_type
+        self.n_gaussians = n_gaussians
+        t = sampling.sample_t(n_gaussians, device)
+        self.sample_t = t[:, None, None]
+        self._xyz = torch.empty(0)
+        self._scaling = torch.empty(0)
+        self._rotation = torch.empty(0)
+        self._opacity = torch.empty(0)
+        self._width = torch.empty(0)
+        self._mask = torch.empty(0)
+        self._curve_points = torch.empty(0)
+        self.is_bezier = torch.empty(0)
+        self.max_radii2D = torch.empty(0)
+        # activations of the base class (scene/gaussian_model.py:38-53)
+        self.scaling_activation = torch.exp
+        self.scaling_inverse_activation = torch.log
+        self.opacity_activation = torch.sigmoid
+        self.inverse_opacity_activation = lambda x: torch.log(x / (1 - x))
+        self.rotation_activation = F.normalize
+
+    # ---- construction ---------------------------------------------------
+    def create_from_curves(self, curve_points, width, opacity_logit, is_bezier=None, mask=None):
+        dev = self.sample_t.device
+        B = curve_points.shape[0]
+        self._curve_points = nn.Parameter(curve_points.to(dev).float().contiguous().requires_grad_(True))
+        self._width = nn.Parameter(width.to(dev).float().view(B, 1).contiguous().requires_grad_(True))
+        self._opacity = nn.Parameter(opacity_logit.to(dev).float().view(B, 1).contiguous().requires_grad_(True))
+        if mask is None:
+            mask = torch.ones((B, self.n_gaussians, 1), device=dev)
+        self._mask = nn.Parameter(mask.to(dev).float().contiguous().requires_grad_(True))
+        self.is_bezier = (torch.ones(B, dtype=torch.bool, device=dev) if is_bezier is None
+                          else is_bezier.to(dev).bool())
+        self.max_radii2D = torch.zeros(B * self.n_gaussians, device=dev)
+        self.prepare_scaling_rot()
+        return self
+
+    def create_from_points(self, points, init_size=0.5):
+        """The geometric part of create_from_pcd (scene/gaussian_curve_model.py:142-178)."""
+        dev = self.sample_t.device
+        pts = points.to(dev).float()
+        dist2 = torch.clamp_min(distCUDA2(pts), 0.0000001)
+        self.dist = torch.sqrt(dist2).mean()
+        bound = init_size * torch.sqrt(dist2).unsqueeze(1)
+        cp = initialize_bezier_curves(pts, bound)
+        n = pts.shape[0]
+        opac = self.inverse_opacity_activation(0.6 * torch.ones((n, 1), dtype=torch.float, device=dev))
+        widths = self.scaling_inverse_activation(5e-3 * torch.ones((n, 1), dtype=torch.float, device=dev))
+        return self.create_from_curves(cp, widths, opac)
+
+    # ---- the hot path -----------------------------------------------------
+    def prepare_scaling_rot(self, eps=1e-8):
+        xyz, rot, scaling = sampling.sample_curves(self._curve_points, self._width, self.is_bezier,
+                                                   self.sample_t.view(-1))
+        self._xyz, self._rotation, self._scaling = xyz, rot, scaling
+
+    # ---- accessors (same names as the reference) -------------------------
+    @property
+    def get_curve_points(self):
+        return self._curve_points
+
+    @property
+    def get_scaling(self):
+        return self._scaling
+
+    @property
+    def get_rotation_matrix(self):
+        return quaternion_to_matrix(self.get_rotation)
+
+    def get_main_axis(self, view_cam):
+        dir_global = self.get_rotation_matrix[..., 0]
+        to_cam = view_cam.camera_center - self._xyz
+        neg_mask = (dir_global * to_cam).sum(-1) < 0.0
+        return torch.where(neg_mask.unsqueeze(-1), -dir_global, dir_global)
+
+    @property
+    def get_opacity(self):
+        return self.opacity_activation(self._opacity.unsqueeze(1).expand(-1, self.n_gaussians, -1).reshape(-1, 1))
+
+    @property
+    def get_curve_opacity(self):
+        return self.opacity_activation(self._opacity)
+
+    @property
+    def get_curve_width(self):
+        return self.scaling_activation(self._width)
+
+    @property
+    def get_rotation(self):
+        return self.rotation_activation(self._rotation)
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    def parameters(self):
+        return [self._curve_points, self._width, self._opacity, self._mask]
