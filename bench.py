@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd views/sec of the curve-Gaussian hot path (BASELINE.json metric).
+
+Workload (config.workload "C4"): 10 000 cubic Beziers x 100 samples = 1 M Gaussians,
+1920x1080, random look-at cameras (seed 0). One STEP = one view through the
+hot path exactly as train.py drives it: prepare_scaling_rot() (curve -> Gaussians) ->
+render() -> 10*(0.9*edge_aware + 0.1*(1-fused_ssim)) -> backward to the curve parameters.
+
+  value : views/s with the ground-truth edge maps already resident in HBM
+  e2e   : the same step through the public API with HOST buffers: the view's edge map comes
+          from pinned host memory every step, the loss and the flat curve gradient go back
+  N>1   : views are sharded over ranks (rank r renders views r::N); every step ends with ONE
+          NCCL all-reduce of the flat curve-parameter gradient (weak scaling)
+  --impl reference : the CPU port of the reference path (oracle/), all host threads, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd views/sec @1M curve-Gaussians 1080p"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--curves", type=int, default=10000)
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--views", type=int, default=16, help="distinct cameras per rank (cycled)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    return ap.parse_args()
+
+
+def config_dict(a, extra=None):
+    c = {"workload": "C4: 10k cubic Beziers x 100 samples = 1M curve-Gaussians, 1920x1080, random look-at cams",
+         "curves": a.curves, "samples_per_curve": a.samples, "gaussians": a.curves * a.samples,
+         "image": f"{a.width}x{a.height}", "step": "1 view/rank: sample -> render -> edge+SSIM loss -> backward",
+         "l2": "per-step working set (~0.9 GB of sorted records + keys) exceeds the 126 MB L2; no flush needed",
+         "parallelism": f"views sharded over {a.gpus} rank(s), one all-reduce of the flat curve gradient per step"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def edge_aware_loss(image, gt_image, threshold=0.1):
+    """Caller-side loss of train.py:101 (utils/loss_utils.py:94-115); not part of the replaced path."""
+    edge_map = gt_image.mean(dim=0, keepdim=True)
+    num_positive = (torch.sum(edge_map > threshold)).float()
+    num_negative = (torch.sum(edge_map <= threshold)).float()
+    mask = torch.where(edge_map > threshold, 5. * (num_negative + 1) / (num_positive + num_negative),
+                       1.0 * (num_positive + 1) / (num_positive + num_negative))
+    return (((image - gt_image) ** 2) * mask).mean()
+
+
+class Pipe:
+    debug = False
+    antialiasing = False
+    render_geo = True
+    compute_cov3D_python = False
+    convert_SHs_python = False
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from curve_gaussian_b200 import _lib, synth
+    from curve_gaussian_b200.curve_model import GaussianCurveModel
+    from curve_gaussian_b200.renderer import render
+    from curve_gaussian_b200.ssim import fused_ssim
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B, n, W, H = a.curves, a.samples, a.width, a.height
+    cp, width, opl, isb = synth.random_curves(B, seed=0)
+    model = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb)
+    bg = torch.zeros(3, device=dev)
+    pipe = Pipe()
+    nviews = max(1, min(a.views, a.steps + a.warmup))
+    cams = [c.to(dev) for c in synth.random_cameras(nviews * world, W, H, seed=0)[rank::world]]
+
+    # ground-truth edge maps: the same curves with control points perturbed by N(0, 0.01^2) (SURVEY 8d ii)
+    g = torch.Generator().manual_seed(123)
+    gt_model = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(
+        cp + 0.01 * torch.randn(cp.shape, generator=g), width, opl, isb)
+    gts_host = []
+    with torch.no_grad():
+        for c in cams:
+            img = render(c, gt_model, pipe, bg)["render"]
+            gts_host.append(img.cpu().pin_memory())
+    del gt_model
+    gts_dev = [t.to(dev) for t in gts_host]
+
+    # one flat fp32 gradient buffer [curve_points | width | opacity | mask]; .grad tensors are views into it,
+    # so backward accumulates in place and the all-reduce needs no pack copy
+    params = [model._curve_points, model._width, model._opacity, model._mask]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    flat_host = torch.empty(flat.shape, dtype=flat.dtype).pin_memory()
+
+    def step(i, host_io):
+        cam = cams[i % len(cams)]
+        flat.zero_()
+        if host_io:
+            gt = gts_host[i % len(cams)].to(dev, non_blocking=True)
+        else:
+            gt = gts_dev[i % len(cams)]
+        model.prepare_scaling_rot()
+        image = render(cam, model, pipe, bg)["render"]
+        Ll1 = edge_aware_loss(image, gt)
+        ssim_value = fused_ssim(image.unsqueeze(0), gt.unsqueeze(0))
+        loss = 10.0 * (0.9 * Ll1 + 0.1 * (1.0 - ssim_value))
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(flat)
+        if host_io:
+            flat_host.copy_(flat, non_blocking=True)
+            return loss.item()
+        return loss
+
+    def timed(host_io, steps, warmup, profile=False):
+        for i in range(warmup):
+            step(i, host_io)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.cg_profile_reset()
+        lib.cg_profile_enable(1 if profile else 0)
+        l0 = lib.cg_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(warmup + i, host_io)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        lib.cg_profile_enable(0)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, lib.cg_launch_count() - l0
+
+    W_, K = max(a.warmup, 3), a.steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(False, K, W_, profile=True)
+    clocks = sampler.stop()
+    stages = _lib.profile_read()
+    ms_e2e, _ = timed(True, K, W_)
+
+    views = K * world
+    value = views / (ms / 1e3)
+    e2e_value = views / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (HBM-bound accounting, SURVEY 8d / DESIGN.md)
+    with torch.no_grad():
+        pk = render(cams[0], model, pipe, bg)
+    P = B * n
+    Npix = W * H
+    from curve_gaussian_b200 import rasterizer as rz
+    R = getattr(rz.rasterize_forward_raw, "last_R", None)
+    per_stage = {k: v[0] / v[1] for k, v in stages.items()}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    alg_bytes = {
+        "blend_bwd": 52 * (R or 0) + 32 * Npix + 48 * P,
+        "blend_fwd": 52 * (R or 0) + 32 * Npix,
+        "radix_sort": (8 + 6 * 24) * (R or 0),
+        "gather_records": (4 + 48 + 48 + 4) * (R or 0),
+        "preprocess_fwd": (44 + 36) * P,
+        "preprocess_bwd": (76 + 40) * P,
+    }
+    dom = max((k for k in per_stage if k in alg_bytes), key=lambda k: stages[k][0], default=None)
+    roofline = None
+    if dom:
+        achieved = alg_bytes[dom] / (per_stage[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "kernel_ms": round(per_stage[dom], 4), "algorithmic_bytes": alg_bytes[dom],
+                    "share_of_step": round(stages[dom][0] / ms, 3)}
+    bytes_view = 264 * P + 148 * (R or 0) + 64 * Npix + 88 * P + 20 * Npix
+    e2e_frac = bytes_view * value / 1e9 / peak
+
+    out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+           "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic (seed 0 curve set + look-at cameras; edge maps rendered from perturbed curves)",
+           "config": config_dict(a, {"num_rendered_R": R, "views_per_rank": len(cams)}),
+           "clocks": clocks,
+           "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e / K, 4),
+                   "h2d_bytes_per_step": int(gts_host[0].numel() * 4 + 2 * 16 * 4),
+                   "d2h_bytes_per_step": int(flat.numel() * 4 + 4)},
+           "gpu_launches": int(launches),
+           "roofline": roofline,
+           "stage_ms": {k: round(v, 4) for k, v in sorted(per_stage.items(), key=lambda kv: -kv[1])},
+           "hbm_algorithmic": {"bytes_per_view": bytes_view, "achieved_GBps": round(bytes_view * value / 1e9 / world, 1),
+                               "frac_of_peak_per_gpu": round(e2e_frac / world, 4)}}
+
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_reference_arm(a, budget_s=a.cpu_budget_s, steps=1, warmup=0)["cpu_baseline"]
+        ref_cuda = time_reference_cuda(model, cams[0], bg, pipe, dev)
+        if ref_cuda:
+            out["reference_cuda_recompiled"] = ref_cuda
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_reference_cuda(model, cam, bg, pipe, dev):
+    """Context only (not a contract key): the UNMODIFIED reference CUDA rasterizer, recompiled for sm_100
+    (oracle/_ref), fwd+bwd on the same view and inputs."""
+    try:
+        from tests import refload
+        ref = refload.ref_rasterizer()
+        if ref is None:
+            return None
+        from curve_gaussian_b200.rasterizer import rasterize_backward_raw, rasterize_forward_raw, GaussianRasterizationSettings
+        with torch.no_grad():
+            m3, op, scl, rot = model.get_xyz, model.get_opacity, model.get_scaling, model.get_rotation
+            col = torch.ones(m3.shape[0], 1, device=dev)
+            axis = model.get_main_axis(cam) @ cam.world_view_transform[:3, :3]
+            amap = torch.cat([axis, torch.ones_like(axis[:, :1])], 1).contiguous()
+        H, W = cam.image_height, cam.image_width
+        tanx, tany = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
+        empty = torch.Tensor([])
+        gc = torch.randn(1, H, W, device=dev)
+        z1, z4 = torch.zeros(1, H, W, device=dev), torch.zeros(4, H, W, device=dev)
+
+        def ref_fb():
+            o = ref.rasterize_gaussians(bg, m3, col, op, scl, rot, 1.0, empty, amap, cam.world_view_transform,
+                                        cam.full_proj_transform, tanx, tany, H, W, empty, 0, cam.camera_center, False,
+                                        False, True, False)
+            ref.rasterize_gaussians_backward(bg, o[7], m3, o[2], col, amap, op, scl, rot, 1.0, empty,
+                                             cam.world_view_transform, cam.full_proj_transform, tanx, tany, gc, z1, z4,
+                                             empty, 0, cam.camera_center, o[3], o[0], o[4], o[5], False, True, False)
+
+        rs = GaussianRasterizationSettings(H, W, tanx, tany, bg, 1.0, cam.world_view_transform, cam.full_proj_transform,
+                                           0, cam.camera_center, False, False, False, True)
+
+        def our_fb():
+            o = rasterize_forward_raw(rs, m3, col, op, scl, rot, None, amap)
+            rasterize_backward_raw(rs, m3, o[2], col, amap, op, scl, rot, None, gc, None, None, o[3], o[0], o[4], o[5])
+
+        def t(fn, it=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(it):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / it
+        r, o = t(ref_fb), t(our_fb)
+        return {"what": "rasterizer fwd+bwd only, same view, same inputs, ms", "reference_ms": round(r, 3),
+                "ours_ms": round(o, 3), "speedup": round(r / o, 2)}
+    except Exception as e:  # context only
+        return {"error": str(e)[:200]}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_arm(a, budget_s, steps, warmup):
+    """The reference path on host cores: torch (CPU) sampling/activations/loss around the C oracle rasterizer
+    (oracle/, OpenMP). Each step is a bounded sample: the per-Gaussian stages for all 1M Gaussians plus the blend
+    passes on the first `rows` rows of tiles, sized to the time budget; views/s is scaled to the full view by the
+    share of tile-instances the sample covered."""
+    from curve_gaussian_b200 import synth
+    from oracle import cpu as O
+    from oracle import cpu_pipeline as CP
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, n, W, H = a.curves, a.samples, a.width, a.height
+    cp, width, opl, isb = synth.random_curves(B, seed=0)
+    cam = synth.random_cameras(1, W, H, seed=0)[0]
+    mask = torch.ones(B, n, 1)
+    gt = torch.zeros(1, H, W)
+    gy = (H + 15) // 16
+    # calibration pass on 2 rows of tiles
+    _, _, t = CP.cpu_train_step(cp, width, opl, mask, isb, n, cam, gt, tile_rows=2)
+    fixed = t["total_s"] - t["blend_fwd_s"] - t["blend_bwd_s"]
+    per_inst = (t["blend_fwd_s"] + t["blend_bwd_s"]) / max(t["R_used"], 1)
+    total_steps = max(steps + warmup, 1)
+    per_step_budget = max(budget_s / total_steps, fixed * 1.2)
+    inst_budget = max((per_step_budget - fixed) / max(per_inst, 1e-12), 1)
+    rows = int(max(1, min(gy, gy * inst_budget / max(t["R_total"], 1))))
+    times, cover = [], []
+    for i in range(total_steps):
+        _, _, tt = CP.cpu_train_step(cp, width, opl, mask, isb, n, cam, gt, tile_rows=rows)
+        if i >= warmup:
+            blend = tt["blend_fwd_s"] + tt["blend_bwd_s"]
+            full = (tt["total_s"] - blend) + blend * tt["R_total"] / max(tt["R_used"], 1)
+            times.append(full)
+            cover.append(tt["R_used"] / max(tt["R_total"], 1))
+    sec = sum(times) / len(times)
+    cores = max(O.num_threads(), torch.get_num_threads())
+    cb = {"value": round(1.0 / sec, 5), "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": (f"1 view of C4 per step: all per-Gaussian stages ({B * n} Gaussians) + blend fwd/bwd on the first {rows} of {gy} "
+                     f"tile rows ({100 * sum(cover) / len(cover):.1f}% of the tile-instances), scaled to the full view"),
+          "seconds_per_view_scaled": round(sec, 3)}
+    return {"cpu_baseline": cb, "ms_per_step": sec * 1e3}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_arm(a, budget_s=90.0, steps=a.steps, warmup=min(a.warmup, 1))
+    cb = r["cpu_baseline"]
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
+           "config": config_dict(a), "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "the reference ships no CPU rasterizer; this is the oracle port of its CUDA path on host cores"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -43,6 +43,12 @@ _SP = C.POINTER(RasterSettings)
 SIGNATURES = {
     "cg_abi_version": (C.c_int, []),
     "cg_last_error": (C.c_char_p, []),
+    "cg_launch_count": (C.c_uint64, []),
+    "cg_profile_enable": (None, [C.c_int]),
+    "cg_profile_reset": (None, []),
+    "cg_profile_stage_count": (C.c_int, []),
+    "cg_profile_stage_name": (C.c_char_p, [C.c_int]),
+    "cg_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "cg_raster_geom_bytes": (_sz, [_i64]),
     "cg_raster_img_bytes": (_sz, [_i32, _i32]),
     "cg_raster_bin_keep_bytes": (_sz, [_i64]),
@@ -86,6 +92,18 @@ def load() -> C.CDLL:
         raise CurveGSError(f"libcurvegs ABI {lib.cg_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = lib
     return lib
+
+
+def profile_read() -> dict:
+    """{stage: (total_ms, calls)} accumulated since the last cg_profile_reset()."""
+    lib = load()
+    out = {}
+    for i in range(lib.cg_profile_stage_count()):
+        ms, n = C.c_double(0), C.c_uint64(0)
+        lib.cg_profile_read(i, C.byref(ms), C.byref(n))
+        if n.value:
+            out[lib.cg_profile_stage_name(i).decode()] = (ms.value, int(n.value))
+    return out
 
 
 def check(rc: int, what: str) -> None:

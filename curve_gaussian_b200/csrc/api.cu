@@ -1,6 +1,9 @@
 // extern "C" entry points of libcurvegs.so (see include/curvegs.h).
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace cg {
@@ -13,6 +16,54 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_profile{0};
+struct ProfRec { int stage; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_pending;
+static std::vector<cudaEvent_t> g_free_events;
+static double g_stage_ms[ST_COUNT];
+static uint64_t g_stage_calls[ST_COUNT];
+
+void count_launches(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
+
+static cudaEvent_t get_event() {
+  if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+StageTimer::StageTimer(int stage_, cudaStream_t st_, int kernels) : stage(stage_), st(st_), rec(nullptr) {
+  count_launches(kernels);
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec* r = new ProfRec{stage, get_event(), get_event()};
+  cudaEventRecord(r->e0, st);
+  rec = r;
+}
+StageTimer::~StageTimer() {
+  if (!rec) return;
+  ProfRec* r = reinterpret_cast<ProfRec*>(rec);
+  cudaEventRecord(r->e1, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_pending.push_back(*r);
+  delete r;
+}
+static void drain_profile() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_pending) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { g_stage_ms[r.stage] += ms; g_stage_calls[r.stage] += 1; }
+    g_free_events.push_back(r.e0);
+    g_free_events.push_back(r.e1);
+  }
+  g_pending.clear();
+}
+static const char* kStageNames[ST_COUNT] = {"sample_fwd", "preprocess_fwd", "scan", "emit_keys", "radix_sort",
+                                            "tile_ranges", "gather_records", "blend_fwd", "blend_bwd",
+                                            "preprocess_bwd", "sample_bwd", "ssim_fwd", "ssim_bwd", "knn"};
 
 int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
                     const float* scales, const float* rotations, const float* cov3D_precomp,
@@ -43,6 +94,21 @@ using namespace cg;
 extern "C" {
 
 int cg_abi_version(void) { return 1; }
+uint64_t cg_launch_count(void) { return g_launches.load(); }
+void cg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+void cg_profile_reset(void) {
+  drain_profile();
+  for (int i = 0; i < ST_COUNT; ++i) { g_stage_ms[i] = 0.0; g_stage_calls[i] = 0; }
+}
+int cg_profile_stage_count(void) { return ST_COUNT; }
+const char* cg_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+int cg_profile_read(int i, double* total_ms, uint64_t* calls) {
+  drain_profile();
+  if (i < 0 || i >= ST_COUNT || !total_ms || !calls) return CG_ERR_ARG;
+  *total_ms = g_stage_ms[i];
+  *calls = g_stage_calls[i];
+  return CG_OK;
+}
 const char* cg_last_error(void) { return g_err; }
 
 size_t cg_raster_geom_bytes(int64_t P) {

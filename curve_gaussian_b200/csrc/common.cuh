@@ -14,6 +14,19 @@ constexpr int TILE_PIX = TILE_X * TILE_Y;
 
 void set_error(const char* fmt, ...);
 
+// Optional per-stage device timing (cudaEvents on the launch stream) and a count of
+// kernels launched by this library; both are read by bench.py through the C ABI.
+enum Stage {
+  ST_SAMPLE_FWD = 0, ST_PREPROCESS_FWD, ST_SCAN, ST_EMIT_KEYS, ST_SORT, ST_TILE_RANGES, ST_GATHER, ST_BLEND_FWD,
+  ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_SAMPLE_BWD, ST_SSIM_FWD, ST_SSIM_BWD, ST_KNN, ST_COUNT
+};
+void count_launches(int n);
+struct StageTimer {
+  int stage; cudaStream_t st; void* rec;
+  StageTimer(int stage_, cudaStream_t st_, int kernels);
+  ~StageTimer();
+};
+
 #define CG_CUDA(expr)                                                        \
   do {                                                                       \
     cudaError_t _e = (expr);                                                 \

@@ -184,6 +184,7 @@ int cg_knn_mean_dist2(int64_t P, const float* points, float* mean_dist2, void* s
                        int(0xff7fffffu ^ 0x7fffffffu)};
   CG_CUDA(cudaMemcpyAsync(ks.bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
   const int rb = int((P + 255) / 256 < 1184 ? (P + 255) / 256 : 1184);
+  StageTimer t_(ST_KNN, st, 4);
   knn_bbox<<<rb, 256, 0, st>>>(P, points, ks.bb);
   CG_LAUNCH_CHECK(0, st);
   knn_morton<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, points, ks.bb, bs.keys[0], bs.vals[0]);

@@ -378,11 +378,13 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   const float fy = H / (2.0f * s->tanfovy), fx = W / (2.0f * s->tanfovx);
   const int64_t nblk = (P + 255) / 256;
+  { StageTimer t_(ST_PREPROCESS_FWD, st, 1);
   preprocess_fwd<<<unsigned(nblk), 256, 0, st>>>(P, means3D, opacities, scales, rotations, cov3D_precomp,
                                                  s->scale_modifier, s->viewmatrix, s->projmatrix, W, H, s->tanfovx,
-                                                 s->tanfovy, fx, fy, gx, gy, s->antialiasing, radii, g);
+                                                 s->tanfovy, fx, fy, gx, gy, s->antialiasing, radii, g); }
   CG_LAUNCH_CHECK(s->debug, st);
-  scan_block_sums<<<1, 1024, 0, st>>>(nblk, g);
+  { StageTimer t_(ST_SCAN, st, 1);
+  scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
   CG_LAUNCH_CHECK(s->debug, st);
   uint32_t total = 0;
   CG_CUDA(cudaMemcpyAsync(&total, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -405,20 +407,26 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
 
   CG_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), st));
   if (R > 0) {
-    emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, gx, bs.keys[0], bs.vals[0]);
+    { StageTimer t_(ST_EMIT_KEYS, st, 1);
+    emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, gx, bs.keys[0], bs.vals[0]); }
     CG_LAUNCH_CHECK(s->debug, st);
     int cur = 0;
     const int end_bit = 32 + int(tile_key_bits(uint32_t(tiles)));
-    int rc = radix_sort_pairs(bs, R, end_bit, &cur, s->debug != 0, st);
+    int rc;
+    { StageTimer t_(ST_SORT, st, 0);
+    rc = radix_sort_pairs(bs, R, end_bit, &cur, s->debug != 0, st); }
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned((R + 255) / 256);
-    tile_ranges<<<rb, 256, 0, st>>>(R, bs.keys[cur], im.ranges);
+    { StageTimer t_(ST_TILE_RANGES, st, 1);
+    tile_ranges<<<rb, 256, 0, st>>>(R, bs.keys[cur], im.ranges); }
     CG_LAUNCH_CHECK(s->debug, st);
+    { StageTimer t_(ST_GATHER, st, 1);
     gather_records<<<rb, 256, 0, st>>>(R, bs.vals[cur], g, colors, s->render_geo ? all_map : nullptr, bk.rec,
-                                       bk.point_list);
+                                       bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   dim3 grid(gx, gy), block(TILE_X, TILE_Y);
+  StageTimer t_blend(ST_BLEND_FWD, st, 1);
   if (s->render_geo)
     blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map, im.final_T,
                                             im.n_contrib, im.tile_maxc);
@@ -431,6 +439,7 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
 
 int launch_mark_visible(int64_t P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t st) {
   if (P == 0) return CG_OK;
+  count_launches(1);
   mark_visible_kernel<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, means3D, vm, present);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;

@@ -354,6 +354,7 @@ int cg_sample_fwd(int64_t B, int32_t n, const float* curve_points, const float* 
   const int64_t P = B * n;
   CG_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(double), st));
   const int rb = int((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
+  StageTimer t_(ST_SAMPLE_FWD, st, 2);
   sample_reduce_fwd<<<rb, 256, 0, st>>>(B, n, curve_points, is_bezier, t, sums);
   CG_LAUNCH_CHECK(0, st);
   sample_fwd_main<<<unsigned((P + 255) / 256), 256, 0, st>>>(B, n, curve_points, width, is_bezier, t, half_step, sums,
@@ -374,6 +375,7 @@ int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* 
   double* sums = reinterpret_cast<double*>(scratch);
   const int64_t P = B * n;
   CG_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(double), st));
+  StageTimer t_(ST_SAMPLE_BWD, st, dL_drotation ? 2 : 1);
   if (dL_drotation) {
     const int rb = int((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
     sample_reduce_bwd<<<rb, 256, 0, st>>>(B, n, curve_points, is_bezier, t, norms, dL_drotation, sums);

@@ -212,6 +212,7 @@ int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
   CG_CUDA(cudaMemsetAsync(b.status, 0, sizeof(uint32_t) * size_t(passes) * ntiles * 256, stream));
 
   int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  count_launches(2 + passes);
   sort_histogram<<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
   sort_scan_bins<<<passes, 256, 0, stream>>>(b.hist);

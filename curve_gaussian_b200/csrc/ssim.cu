@@ -166,6 +166,7 @@ int cg_ssim_fwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
          "the three partial maps come together");
   CG_ARG(int64_t(B) * CH <= 65535, "B*CH");
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, B * CH);
+  StageTimer t_(ST_SSIM_FWD, reinterpret_cast<cudaStream_t>(stream), 1);
   ssim_fwd_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(H, W, C1, C2, img1, img2, ssim_map,
                                                                          dm_dmu1, dm_dsigma1_sq, dm_dsigma12);
   CG_LAUNCH_CHECK(0, reinterpret_cast<cudaStream_t>(stream));
@@ -181,6 +182,7 @@ int cg_ssim_bwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
   CG_ARG(img1 && img2 && dL_dmap && dm_dmu1 && dm_dsigma1_sq && dm_dsigma12 && dL_dimg1, "ssim_bwd pointers");
   CG_ARG(int64_t(B) * CH <= 65535, "B*CH");
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, B * CH);
+  StageTimer t_(ST_SSIM_BWD, reinterpret_cast<cudaStream_t>(stream), 1);
   ssim_bwd_kernel<<<grid, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(H, W, img1, img2, dL_dmap, dm_dmu1,
                                                                          dm_dsigma1_sq, dm_dsigma12, dL_dimg1);
   CG_LAUNCH_CHECK(0, reinterpret_cast<cudaStream_t>(stream));

@@ -122,6 +122,7 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
                    "cg_raster_fwd_blend")
     # keep scratch reachable for debug_fetch of the sorted keys
     rasterize_forward_raw.last_scratch = bin_scratch
+    rasterize_forward_raw.last_R = R
     return R, color, radii, geom, bin_keep, img, invdepth, out_all_map
 
 

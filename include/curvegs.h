@@ -41,6 +41,16 @@ int cg_abi_version(void);
 /* Thread-local text of the last error returned on this thread. */
 const char* cg_last_error(void);
 
+/* Instrumentation (used by bench.py): number of kernels this library has launched
+ * since load, and optional per-stage device timing with CUDA events recorded on the
+ * launch stream. cg_profile_read synchronizes on the recorded events. */
+uint64_t cg_launch_count(void);
+void cg_profile_enable(int on);
+void cg_profile_reset(void);
+int cg_profile_stage_count(void);
+const char* cg_profile_stage_name(int stage);
+int cg_profile_read(int stage, double* total_ms, uint64_t* calls);
+
 /* ------------------------------------------------------------------ */
 /* Rasterizer (reference: diff_cur_rasterization._C)                   */
 /* ------------------------------------------------------------------ */
