@@ -63,7 +63,8 @@ static void drain_profile() {
 }
 static const char* kStageNames[ST_COUNT] = {"sample_fwd", "preprocess_fwd", "scan", "emit_keys", "radix_sort",
                                             "tile_ranges", "gather_records", "blend_fwd", "blend_bwd",
-                                            "preprocess_bwd", "sample_bwd", "ssim_fwd", "ssim_bwd", "knn"};
+                                            "preprocess_bwd", "sample_bwd", "ssim_fwd", "ssim_bwd", "knn",
+                                            "activate_fwd", "activate_bwd"};
 
 int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
                     const float* scales, const float* rotations, const float* cov3D_precomp,

@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...);
 // kernels launched by this library; both are read by bench.py through the C ABI.
 enum Stage {
   ST_SAMPLE_FWD = 0, ST_PREPROCESS_FWD, ST_SCAN, ST_EMIT_KEYS, ST_SORT, ST_TILE_RANGES, ST_GATHER, ST_BLEND_FWD,
-  ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_SAMPLE_BWD, ST_SSIM_FWD, ST_SSIM_BWD, ST_KNN, ST_COUNT
+  ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_SAMPLE_BWD, ST_SSIM_FWD, ST_SSIM_BWD, ST_KNN, ST_ACTIVATE_FWD, ST_ACTIVATE_BWD, ST_COUNT
 };
 void count_launches(int n);
 struct StageTimer {

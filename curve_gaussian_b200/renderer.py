@@ -6,7 +6,17 @@ import math
 
 import torch
 
+from .activation import curve_activate
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+
+def _can_fuse(pc) -> bool:
+    """The fused activation needs the curve model's raw tensors (the reference class has them too)."""
+    need = ("_xyz", "_rotation", "_scaling", "_opacity", "_mask", "n_gaussians")
+    if not all(hasattr(pc, k) for k in need) or getattr(pc, "fuse_activations", True) is False:
+        return False
+    P = pc._xyz.shape[0]
+    return pc._xyz.is_cuda and pc._opacity.numel() * pc.n_gaussians == P and pc._mask.numel() == P
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, separate_sh=False,
@@ -41,20 +51,25 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
     means3D = pc.get_xyz
     means2D = screenspace_points
-    opacity = pc.get_opacity
-    scales = pc.get_scaling
-    rotations = pc.get_rotation
-    if use_mask:
-        sm = torch.sigmoid(pc._mask)
-        mask = ((sm > mask_thr).float() - sm).detach() + sm
-        scales = pc.get_scaling * mask.view(-1, 1)
-        opacity = pc.get_opacity * mask.view(-1, 1)
-
     dev = means3D.device
     colors_precomp = torch.ones(means3D.shape[0], 1, device=dev)
-    global_normal = pc.get_main_axis(viewpoint_camera)
-    local_normal = global_normal @ viewpoint_camera.world_view_transform[:3, :3]
-    input_all_map = torch.cat([local_normal, torch.ones_like(local_normal[:, :1])], dim=1)
+    if _can_fuse(pc):
+        # one fused kernel for normalize / sigmoid / mask straight-through / main axis / all_map
+        rotations, opacity, scales, input_all_map = curve_activate(
+            pc._xyz, pc._rotation, pc._scaling, pc._opacity, pc._mask, pc.n_gaussians,
+            viewpoint_camera.camera_center, viewpoint_camera.world_view_transform, use_mask, mask_thr)
+    else:
+        opacity = pc.get_opacity
+        scales = pc.get_scaling
+        rotations = pc.get_rotation
+        if use_mask:
+            sm = torch.sigmoid(pc._mask)
+            mask = ((sm > mask_thr).float() - sm).detach() + sm
+            scales = pc.get_scaling * mask.view(-1, 1)
+            opacity = pc.get_opacity * mask.view(-1, 1)
+        global_normal = pc.get_main_axis(viewpoint_camera)
+        local_normal = global_normal @ viewpoint_camera.world_view_transform[:3, :3]
+        input_all_map = torch.cat([local_normal, torch.ones_like(local_normal[:, :1])], dim=1)
 
     rendered_image, radii, depth_image, out_all_map = rasterizer(
         means3D=means3D, means2D=means2D, shs=None, colors_precomp=colors_precomp, opacities=opacity,

@@ -167,6 +167,25 @@ int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* 
                   float* dL_dcurve_points, float* dL_dwidth,
                   void* scratch, void* stream);
 
+/* Per-view activations render() applies before rasterizing
+ * (gaussian_renderer/__init__.py:57-104, scene/gaussian_curve_model.py:99-122):
+ *   rot_n = normalize(rotation), opacity = sigmoid(opacity_logit[b]) (x mask),
+ *   scales = scaling (x mask), mask = straight-through 1[sigmoid(mask_logit) > thr]
+ *   (mask_logit NULL = use_mask False), all_map = (view-space main axis facing the
+ *   camera, 1). opacity_logit is (B), mask_logit (B*n); outputs are per Gaussian.
+ * The backward returns gradients for rotation, scaling, opacity_logit (B) and
+ * mask_logit (B*n); xyz only decides a sign and receives none. Upstream grads may be NULL. */
+int cg_activate_fwd(int64_t B, int32_t n, const float* xyz, const float* rotation, const float* scaling,
+                    const float* opacity_logit, const float* mask_logit, float mask_thr,
+                    const float* campos, const float* viewmatrix,
+                    float* rot_n, float* opacity, float* scales, float* all_map, void* stream);
+int cg_activate_bwd(int64_t B, int32_t n, const float* xyz, const float* rotation, const float* scaling,
+                    const float* opacity_logit, const float* mask_logit, float mask_thr,
+                    const float* campos, const float* viewmatrix,
+                    const float* g_rot_n, const float* g_opacity, const float* g_scales, const float* g_all_map,
+                    float* g_rotation, float* g_scaling, float* g_opacity_logit, float* g_mask_logit,
+                    void* stream);
+
 /* ------------------------------------------------------------------ */
 /* Fused SSIM (reference: submodules/fused-ssim)                        */
 /* ------------------------------------------------------------------ */

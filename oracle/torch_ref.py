@@ -79,7 +79,7 @@ def sample_curves(curve_points, width, is_bezier, n, eps=1e-8):
     xyz = xyz.permute(1, 0, 2).reshape(B * n, 3)                  # 'm b c -> (b m) c'
     tangent = tangent.permute(1, 0, 2).reshape(B * n, 3)
     v0 = tangent / (torch.linalg.vector_norm(tangent, dim=-1, keepdim=True) + eps)
-    up = torch.tensor([[0.0, 0.0, 1.0]], device=dev)
+    up = torch.tensor([[0.0, 0.0, 1.0]], device=dev, dtype=tangent.dtype)
     v1 = torch.linalg.cross(tangent, up.expand_as(tangent), dim=-1)
     v1 = v1 / torch.norm(v1)                                      # whole-tensor norm (:190)
     v2 = torch.linalg.cross(tangent, v1, dim=-1)
