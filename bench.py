@@ -169,12 +169,9 @@ def run_ours(a):
 
     # one flat fp32 gradient buffer [curve_points | width | opacity | mask]; .grad tensors are views into it,
     # so backward accumulates in place and the all-reduce needs no pack copy
-    params = [model._curve_points, model._width, model._opacity, model._mask]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    from curve_gaussian_b200.parallel import FlatGrad
+    fg = FlatGrad([model._curve_points, model._width, model._opacity, model._mask])
+    flat = fg.flat
     flat_host = torch.empty(flat.shape, dtype=flat.dtype).pin_memory()
 
     def step(i, host_io):
@@ -190,8 +187,7 @@ def run_ours(a):
         ssim_value = fused_ssim(image.unsqueeze(0), gt.unsqueeze(0))
         loss = 10.0 * (0.9 * Ll1 + 0.1 * (1.0 - ssim_value))
         loss.backward()
-        if world > 1:
-            dist.all_reduce(flat)
+        fg.all_reduce()
         if host_io:
             flat_host.copy_(flat, non_blocking=True)
             return loss.item()
