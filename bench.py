@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--views", type=int, default=16, help="distinct cameras per rank (cycled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="spell the loss as train.py does (torch edge_aware_loss + fused_ssim) instead of the fused op")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
 
@@ -53,6 +55,7 @@ def config_dict(a, extra=None):
     c = {"workload": "C4: 10k cubic Beziers x 100 samples = 1M curve-Gaussians, 1920x1080, random look-at cams",
          "curves": a.curves, "samples_per_curve": a.samples, "gaussians": a.curves * a.samples,
          "image": f"{a.width}x{a.height}", "step": "1 view/rank: sample -> render -> edge+SSIM loss -> backward",
+         "loss": "unfused (torch edge_aware_loss + fused_ssim)" if a.unfused_loss else "fused edge+SSIM loss op",
          "l2": "per-step working set (~0.9 GB of sorted records + keys) exceeds the 126 MB L2; no flush needed",
          "parallelism": f"views sharded over {a.gpus} rank(s), one all-reduce of the flat curve gradient per step"}
     if extra:
@@ -133,6 +136,7 @@ def run_ours(a):
     import torch.distributed as dist
     from curve_gaussian_b200 import _lib, synth
     from curve_gaussian_b200.curve_model import GaussianCurveModel
+    from curve_gaussian_b200.loss import edge_ssim_loss
     from curve_gaussian_b200.renderer import render
     from curve_gaussian_b200.ssim import fused_ssim
 
@@ -185,9 +189,13 @@ def run_ours(a):
             gt = gts_dev[i % len(cams)]
         model.prepare_scaling_rot()
         image = render(cam, model, pipe, bg)["render"]
-        Ll1 = edge_aware_loss(image, gt)
-        ssim_value = fused_ssim(image.unsqueeze(0), gt.unsqueeze(0))
-        loss = 10.0 * (0.9 * Ll1 + 0.1 * (1.0 - ssim_value))
+        if a.unfused_loss:
+            Ll1 = edge_aware_loss(image, gt)
+            ssim_value = fused_ssim(image.unsqueeze(0), gt.unsqueeze(0))
+            loss = 10.0 * (0.9 * Ll1 + 0.1 * (1.0 - ssim_value))
+        else:
+            # the same scalar (train.py:101-107) as one fused forward + one fused backward kernel
+            loss = edge_ssim_loss(image, gt, threshold=0.1, lambda_mse=10.0, lambda_dssim=0.1)
         loss.backward()
         fg.all_reduce()
         if host_io:

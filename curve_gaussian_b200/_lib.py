@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcurvegs.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class RasterSettings(C.Structure):
@@ -52,7 +52,7 @@ SIGNATURES = {
     "cg_raster_geom_bytes": (_sz, [_i64]),
     "cg_raster_img_bytes": (_sz, [_i32, _i32]),
     "cg_raster_bin_keep_bytes": (_sz, [_i64]),
-    "cg_raster_bin_scratch_bytes": (_sz, [_i64]),
+    "cg_raster_bin_scratch_bytes": (_sz, [_i64, _i64]),
     "cg_raster_bwd_scratch_bytes": (_sz, [_i64]),
     "cg_raster_fwd_geom": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
     "cg_raster_fwd_blend": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -66,6 +66,10 @@ SIGNATURES = {
     "cg_activate_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp] + [_vp] * 9),
     "cg_ssim_fwd": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_ssim_bwd": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_edge_ssim_loss_stats_bytes": (_sz, []),
+    "cg_edge_ssim_loss_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_edge_ssim_loss_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_rotate_channels": (C.c_int, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "cg_knn_scratch_bytes": (_sz, [_i64]),
     "cg_knn_mean_dist2": (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
 }

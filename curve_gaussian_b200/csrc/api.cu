@@ -64,7 +64,7 @@ static void drain_profile() {
 static const char* kStageNames[ST_COUNT] = {"sample_fwd", "preprocess_fwd", "scan", "emit_keys", "radix_sort",
                                             "tile_ranges", "gather_records", "blend_fwd", "blend_bwd",
                                             "preprocess_bwd", "sample_bwd", "ssim_fwd", "ssim_bwd", "knn",
-                                            "activate_fwd", "activate_bwd"};
+                                            "activate_fwd", "activate_bwd", "loss_fwd", "loss_bwd"};
 
 int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
                     const float* scales, const float* rotations, const float* cov3D_precomp,
@@ -79,6 +79,8 @@ int launch_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* m
                float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
                float* dL_drotations, float* dL_dall_map_in, cudaStream_t st);
 int launch_mark_visible(int64_t P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t st);
+int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, const void* bin_keep,
+                        const void* bin_scratch, uint64_t* dst, cudaStream_t st);
 
 static int check_settings(const cg_raster_settings* s) {
   CG_ARG(s != nullptr, "settings");
@@ -94,7 +96,7 @@ using namespace cg;
 
 extern "C" {
 
-int cg_abi_version(void) { return 1; }
+int cg_abi_version(void) { return 2; }
 uint64_t cg_launch_count(void) { return g_launches.load(); }
 void cg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 void cg_profile_reset(void) {
@@ -127,9 +129,9 @@ size_t cg_raster_bin_keep_bytes(int64_t R) {
   BinKeep::carve(nullptr, R < 0 ? 0 : R, &b);
   return b;
 }
-size_t cg_raster_bin_scratch_bytes(int64_t R) {
+size_t cg_raster_bin_scratch_bytes(int64_t P, int64_t R) {
   size_t b = 0;
-  BinScratch::carve(nullptr, R < 0 ? 0 : R, &b);
+  BinScratch::carve(nullptr, P < 0 ? 0 : P, R < 0 ? 0 : R, &b);
   return b;
 }
 size_t cg_raster_bwd_scratch_bytes(int64_t P) { return size_t(P < 1 ? 1 : P) * 8 * sizeof(float); }
@@ -216,14 +218,11 @@ int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
   GeomState g = GeomState::carve(const_cast<void*>(geom), P, nullptr);
   ImgState im = ImgState::carve(const_cast<void*>(img), W, H, nullptr);
   BinKeep bk = BinKeep::carve(const_cast<void*>(bin_keep), R, nullptr);
-  BinScratch bs = BinScratch::carve(const_cast<void*>(bin_scratch), R, nullptr);
   switch (which) {
-    case 0: {
-      int passes = (32 + int(tile_key_bits(uint32_t(tiles))) + 7) / 8;
-      if (passes > SORT_MAX_PASSES) passes = SORT_MAX_PASSES;
-      CG_ARG(bin_scratch != nullptr, "bin_scratch");
-      src = bs.keys[passes & 1]; bytes = size_t(R) * 8; break;
-    }
+    case 0:
+      // the reference's 64-bit keys are not materialised (see BinScratch); rebuild them from the sorted state
+      CG_ARG(bin_scratch != nullptr && bin_keep != nullptr && geom != nullptr, "bin_scratch/bin_keep/geom");
+      return launch_rebuild_keys(P, R, W, H, geom, bin_keep, bin_scratch, reinterpret_cast<uint64_t*>(dst), st);
     case 1: CG_ARG(bin_keep != nullptr, "bin_keep"); src = bk.point_list; bytes = size_t(R) * 4; break;
     case 2: src = im.ranges; bytes = tiles * 8; break;
     case 3: src = g.tiles; bytes = size_t(P) * 4; break;

@@ -18,7 +18,8 @@ void set_error(const char* fmt, ...);
 // kernels launched by this library; both are read by bench.py through the C ABI.
 enum Stage {
   ST_SAMPLE_FWD = 0, ST_PREPROCESS_FWD, ST_SCAN, ST_EMIT_KEYS, ST_SORT, ST_TILE_RANGES, ST_GATHER, ST_BLEND_FWD,
-  ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_SAMPLE_BWD, ST_SSIM_FWD, ST_SSIM_BWD, ST_KNN, ST_ACTIVATE_FWD, ST_ACTIVATE_BWD, ST_COUNT
+  ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_SAMPLE_BWD, ST_SSIM_FWD, ST_SSIM_BWD, ST_KNN, ST_ACTIVATE_FWD, ST_ACTIVATE_BWD,
+  ST_LOSS_FWD, ST_LOSS_BWD, ST_COUNT
 };
 void count_launches(int n);
 struct StageTimer {
@@ -125,11 +126,13 @@ struct ImgState {
 struct BinKeep {
   Rec* rec;
   uint32_t* point_list;
+  float4* cull;   // per instance {x, y, hx, hy}: conservative box of the pixels it can contribute to
   static BinKeep carve(void* base, int64_t R, size_t* bytes) {
     Carver c(base);
     BinKeep b;
     b.rec = c.take<Rec>(R + 1);
     b.point_list = c.take<uint32_t>(R + 1);
+    b.cull = c.take<float4>(R + 1);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }
@@ -141,25 +144,45 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
 constexpr int SORT_MAX_PASSES = 8;
 
-struct BinScratch {
-  uint64_t* keys[2];
+// Ping-pong buffers + look-back state of one radix sort of n (key, value) pairs.
+template <typename K>
+struct SortBufs {
+  K* keys[2];
   uint32_t* vals[2];
   uint32_t* hist;     // [SORT_MAX_PASSES][256] global digit histograms -> exclusive bases
   uint32_t* ticket;   // [SORT_MAX_PASSES] dynamic tile id counters
   uint32_t* status;   // [passes][ntiles][256] decoupled look-back words
   size_t status_words;
-  static BinScratch carve(void* base, int64_t R, size_t* bytes) {
-    Carver c(base);
-    BinScratch b;
-    int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
-    b.keys[0] = c.take<uint64_t>(R + 1);
-    b.keys[1] = c.take<uint64_t>(R + 1);
-    b.vals[0] = c.take<uint32_t>(R + 1);
-    b.vals[1] = c.take<uint32_t>(R + 1);
+  static SortBufs carve(Carver& c, int64_t n) {
+    SortBufs b;
+    int64_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+    b.keys[0] = c.take<K>(n + 1);
+    b.keys[1] = c.take<K>(n + 1);
+    b.vals[0] = c.take<uint32_t>(n + 1);
+    b.vals[1] = c.take<uint32_t>(n + 1);
     b.hist = c.take<uint32_t>(SORT_MAX_PASSES * 256);
     b.ticket = c.take<uint32_t>(32);
-    b.status_words = size_t(SORT_MAX_PASSES) * size_t(ntiles > 0 ? ntiles : 1) * 256;
+    b.status_words = size_t(sizeof(K)) * size_t(ntiles > 0 ? ntiles : 1) * 256;   // sizeof(K) = max passes
     b.status = c.take<uint32_t>(b.status_words);
+    return b;
+  }
+};
+
+// Forward-only scratch of the binning step.
+//   gs: the P Gaussians sorted by the bits of their view-space depth (value = Gaussian index)
+//   is: the R tile-instances, emitted in that depth order, sorted by tile index only
+// A stable sort by tile of a list that is already in (depth, index) order is the
+// (tile, depth) order with ties in emission = index order, i.e. exactly the permutation the
+// reference gets from one 64-bit sort of tile<<32|depth (rasterizer_impl.cu:70-111, :309-314),
+// but the big R-sized passes shrink from 6 x 24 B to 2 x 16 B per instance.
+struct BinScratch {
+  SortBufs<uint32_t> gs;
+  SortBufs<uint32_t> is;
+  static BinScratch carve(void* base, int64_t P, int64_t R, size_t* bytes) {
+    Carver c(base);
+    BinScratch b;
+    b.gs = SortBufs<uint32_t>::carve(c, P);
+    b.is = SortBufs<uint32_t>::carve(c, R);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }
@@ -175,7 +198,9 @@ inline uint32_t tile_key_bits(uint32_t n) {
   return bits ? bits : 1;
 }
 
-int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
-                     bool debug, cudaStream_t stream);
+// Stable LSD radix sort of b.keys[0]/b.vals[0] on bits [0,end_bit); *out_buf tells which of the
+// two ping-pong buffers holds the result. Instantiated for uint32_t and uint64_t keys (sort.cu).
+template <typename K>
+int radix_sort_pairs(const SortBufs<K>& b, int64_t n, int end_bit, int* out_buf, bool debug, cudaStream_t stream);
 
 }  // namespace cg

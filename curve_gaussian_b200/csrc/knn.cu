@@ -151,9 +151,9 @@ struct KnnScratch {
     KnnScratch k;
     k.bb = c.take<float>(32);
     k.boxes = c.take<Box>((P + BOX - 1) / BOX + 1);
-    size_t sb = 0;
-    BinScratch::carve(nullptr, P, &sb);
-    k.sort = c.take<char>(sb);
+    Carver sc(nullptr);
+    SortBufs<uint64_t>::carve(sc, P);
+    k.sort = c.take<char>((sc.used + 127) & ~size_t(127));
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return k;
   }
@@ -178,7 +178,8 @@ int cg_knn_mean_dist2(int64_t P, const float* points, float* mean_dist2, void* s
   CG_ARG(points && mean_dist2 && scratch, "knn pointers");
   CG_ARG((reinterpret_cast<uintptr_t>(scratch) & 127u) == 0, "scratch must be 128-byte aligned");
   KnnScratch ks = KnnScratch::carve(scratch, P, nullptr);
-  BinScratch bs = BinScratch::carve(ks.sort, P, nullptr);
+  Carver sc(ks.sort);
+  SortBufs<uint64_t> bs = SortBufs<uint64_t>::carve(sc, P);
   // bbox init: +max / -max in the ordered-int domain
   const int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, int(0xff7fffffu ^ 0x7fffffffu), int(0xff7fffffu ^ 0x7fffffffu),
                        int(0xff7fffffu ^ 0x7fffffffu)};
@@ -190,7 +191,7 @@ int cg_knn_mean_dist2(int64_t P, const float* points, float* mean_dist2, void* s
   knn_morton<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, points, ks.bb, bs.keys[0], bs.vals[0]);
   CG_LAUNCH_CHECK(0, st);
   int cur = 0;
-  int rc = radix_sort_pairs(bs, P, 32, &cur, false, st);
+  int rc = radix_sort_pairs<uint64_t>(bs, P, 32, &cur, false, st);
   if (rc != CG_OK) return rc;
   const unsigned nbox = unsigned((P + BOX - 1) / BOX);
   knn_boxes<<<nbox, BOX, 0, st>>>(P, points, bs.vals[cur], ks.boxes);

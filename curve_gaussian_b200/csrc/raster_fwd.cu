@@ -160,14 +160,43 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
   if (threadIdx.x == 0) g.total[0] = s_carry;
 }
 
-// One (key,value) per overlapped tile, row-major over the rect, key =
-// tile<<32 | float_bits(depth) (rasterizer_impl.cu:70-111).
+// Per-Gaussian sort input: key = bits of the view-space depth (culled Gaussians emit nothing,
+// their key only has to be deterministic), value = Gaussian index.
 __global__ void __launch_bounds__(256)
-emit_keys(int64_t P, GeomState g, int grid_x, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+init_depth_keys(int64_t P, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= P) return;
+  keys[i] = g.tiles[i] ? __float_as_uint(g.depth[i]) : 0xffffffffu;
+  vals[i] = uint32_t(i);
+}
+
+// Block sums of tiles_touched taken in depth order (perm = Gaussian indices sorted by depth).
+__global__ void __launch_bounds__(256)
+perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
+  __shared__ uint32_t s_wsum[8];
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  uint32_t v = (i < P) ? g.tiles[perm[i]] : 0u;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i2 = 0; i2 < 8; ++i2) t += s_wsum[i2];
+    g.blk_sum[blockIdx.x] = t;
+  }
+}
+
+// One (tile, Gaussian) pair per overlapped tile, row-major over the rect like
+// rasterizer_impl.cu:70-111, but Gaussians are visited in depth order and the key is the
+// tile index alone (see BinScratch). Slot i of the scan is Gaussian perm[i].
+__global__ void __launch_bounds__(256)
+emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x, uint32_t* __restrict__ keys,
+          uint32_t* __restrict__ vals) {
   __shared__ uint32_t s_w[8];
-  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t cnt = (idx < P) ? g.tiles[idx] : 0u;
+  const uint32_t idx = (i < P) ? perm[i] : 0u;
+  const uint32_t cnt = (i < P) ? g.tiles[idx] : 0u;
   uint32_t inc = cnt;
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
@@ -176,37 +205,53 @@ emit_keys(int64_t P, GeomState g, int grid_x, uint64_t* __restrict__ keys, uint3
   if (lane == 31) s_w[w] = inc;
   __syncthreads();
   uint32_t off = g.blk_prefix[blockIdx.x] + inc - cnt;
-  for (uint32_t i = 0; i < w; ++i) off += s_w[i];
+  for (uint32_t k = 0; k < w; ++k) off += s_w[k];
   if (cnt == 0) return;
   const uint2 rc = g.rect[idx];
   const uint32_t mnx = rc.x & 0xffffu, mny = rc.x >> 16, mxx = rc.y & 0xffffu, mxy = rc.y >> 16;
-  const uint32_t dbits = __float_as_uint(g.depth[idx]);
   for (uint32_t y = mny; y < mxy; ++y)
     for (uint32_t x = mnx; x < mxx; ++x) {
-      keys[off] = (uint64_t(y * uint32_t(grid_x) + x) << 32) | dbits;
-      vals[off] = uint32_t(idx);
+      keys[off] = y * uint32_t(grid_x) + x;
+      vals[off] = idx;
       ++off;
     }
 }
 
 __global__ void __launch_bounds__(256)
-tile_ranges(int64_t R, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+tile_ranges(int64_t R, const uint32_t* __restrict__ tiles_sorted, uint2* __restrict__ ranges) {
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
-  const uint32_t cur = uint32_t(keys[i] >> 32);
+  const uint32_t cur = tiles_sorted[i];
   if (i == 0) ranges[cur].x = 0;
   else {
-    const uint32_t prev = uint32_t(keys[i - 1] >> 32);
+    const uint32_t prev = tiles_sorted[i - 1];
     if (cur != prev) { ranges[prev].y = uint32_t(i); ranges[cur].x = uint32_t(i); }
   }
   if (i == R - 1) ranges[cur].y = uint32_t(R);
 }
 
-// Sorted instance i -> contiguous 48-byte record + point list entry.
+// The reference's 64-bit sort keys, rebuilt for parity checks: tile<<32 | float_bits(depth).
+__global__ void __launch_bounds__(256)
+rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_t* __restrict__ point_list,
+             const float* __restrict__ depth, uint64_t* __restrict__ keys) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= R) return;
+  keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
+}
+
+// Sorted instance i -> contiguous 48-byte record + point list entry + cull box.
+//
+// The cull box {x, y, hx, hy} bounds, conservatively, the pixels this instance can
+// contribute to. A pixel contributes only if alpha = min(0.99, o*exp(power)) >= 1/255
+// (forward.cu:361-363), i.e. power >= -tau with tau = ln(255*o); {d : 0.5 d^T Q d <= tau}
+// is an ellipse whose axis-aligned half extents are sqrt(2 tau Sxx), sqrt(2 tau Syy) with
+// S = Q^-1. The box is inflated (1e-4 relative + 0.05 px) far beyond the fp32 error of
+// `power`, and degenerate inputs (NaN, non-positive-definite conic) get an infinite box, so
+// skipping an instance whose box misses a warp's pixel block never changes a result bit.
 __global__ void __launch_bounds__(256)
 gather_records(int64_t R, const uint32_t* __restrict__ sorted_vals, GeomState g,
                const float* __restrict__ colors, const float* __restrict__ all_map,
-               Rec* __restrict__ rec, uint32_t* __restrict__ point_list) {
+               Rec* __restrict__ rec, uint32_t* __restrict__ point_list, float4* __restrict__ cull) {
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
   const uint32_t id = sorted_vals[i];
@@ -219,6 +264,12 @@ gather_records(int64_t R, const uint32_t* __restrict__ sorted_vals, GeomState g,
   out[0] = make_float4(xy.x, xy.y, co.x, co.y);
   out[1] = make_float4(co.z, co.w, __ldg(colors + id), 1.f / g.depth[id]);
   out[2] = mp;
+  const float det_q = co.x * co.z - co.y * co.y;
+  const float tau = fmaxf(logf(255.0f * co.w), 0.0f);   // NaN (o <= 0) -> 0: only d == 0 could ever pass
+  float hx = sqrtf(2.0f * tau * (co.z / det_q)) * 1.0001f + 0.05f;
+  float hy = sqrtf(2.0f * tau * (co.x / det_q)) * 1.0001f + 0.05f;
+  if (!(det_q > 0.0f) || !(hx >= 0.0f) || !(hy >= 0.0f)) hx = hy = __int_as_float(0x7f800000);
+  cull[i] = make_float4(xy.x, xy.y, hx, hy);
 }
 
 // ---------------------------------------------------------------------------
@@ -255,25 +306,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 constexpr int BATCH = 256;
 
-// One CTA per 16x16 tile, one thread per pixel. The tile's sorted records are a
-// contiguous span; thread 0 streams it into a 2-deep shared ring with
-// cp.async.bulk while all threads blend the previous batch.
+// One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block. The tile's
+// sorted records (and their cull boxes) are contiguous spans; thread 0 streams them into a
+// 2-deep shared ring with cp.async.bulk while all threads blend the previous batch.
+// Each warp first tests 32 cull boxes at a time (one per lane) against its pixel block and
+// only walks the instances whose box overlaps it, in list order (forward.cu:331-396 semantics).
 template <bool GEO>
 __global__ void __launch_bounds__(256)
-blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, int H,
-          const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
+blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, const float4* __restrict__ cull,
+          int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
           uint32_t* __restrict__ tile_maxc) {
   __shared__ __align__(128) Rec s_rec[2][BATCH];
+  __shared__ __align__(16) float4 s_cull[2][BATCH];
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ uint32_t s_maxc;
 
   const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const uint32_t tid = threadIdx.y * TILE_X + threadIdx.x;
-  const uint32_t pix_x = blockIdx.x * TILE_X + threadIdx.x, pix_y = blockIdx.y * TILE_Y + threadIdx.y;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  const uint32_t blk_x = blockIdx.x * TILE_X + (warp & 1) * 8, blk_y = blockIdx.y * TILE_Y + (warp >> 1) * 4;
+  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
   const bool inside = pix_x < uint32_t(W) && pix_y < uint32_t(H);
   const uint32_t pix_id = uint32_t(W) * pix_y + pix_x;
   const float pxf = float(pix_x), pyf = float(pix_y);
+  // pixel block of this warp, clipped to the image
+  const float bx0 = float(blk_x), bx1 = float(min(blk_x + 7u, uint32_t(W) - 1u));
+  const float by0 = float(blk_y), by1 = float(min(blk_y + 3u, uint32_t(H) - 1u));
   const uint2 range = ranges[tile];
   const int total = int(range.y - range.x);
   const int rounds = (total + BATCH - 1) / BATCH;
@@ -286,15 +345,16 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, 
   }
   __syncthreads();
   if (tid == 0 && rounds > 0) {
-    const uint32_t bytes = uint32_t(min(BATCH, total)) * uint32_t(sizeof(Rec));
-    mbar_expect_tx(&s_full[0], bytes);
-    bulk_g2s(&s_rec[0][0], rec + range.x, bytes, &s_full[0]);
+    const uint32_t nb = uint32_t(min(BATCH, total));
+    mbar_expect_tx(&s_full[0], nb * uint32_t(sizeof(Rec) + sizeof(float4)));
+    bulk_g2s(&s_rec[0][0], rec + range.x, nb * uint32_t(sizeof(Rec)), &s_full[0]);
+    bulk_g2s(&s_cull[0][0], cull + range.x, nb * uint32_t(sizeof(float4)), &s_full[0]);
   }
 
   bool done = !inside;
   float T = 1.0f, C = 0.f, invd_acc = 0.f;
   float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3v = 0.f;
-  uint32_t contributor = 0, last_contributor = 0;
+  uint32_t last_contributor = 0;
 
   int todo = total;
   for (int b = 0; b < rounds; ++b, todo -= BATCH) {
@@ -305,37 +365,58 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, 
       break;
     }
     if (tid == 0 && b + 1 < rounds) {
-      const int nb = min(BATCH, todo - BATCH);
-      const uint32_t bytes = uint32_t(nb) * uint32_t(sizeof(Rec));
-      mbar_expect_tx(&s_full[(b + 1) & 1], bytes);
-      bulk_g2s(&s_rec[(b + 1) & 1][0], rec + range.x + size_t(b + 1) * BATCH, bytes, &s_full[(b + 1) & 1]);
+      const uint32_t nb = uint32_t(min(BATCH, todo - BATCH));
+      const size_t off = size_t(range.x) + size_t(b + 1) * BATCH;
+      mbar_expect_tx(&s_full[(b + 1) & 1], nb * uint32_t(sizeof(Rec) + sizeof(float4)));
+      bulk_g2s(&s_rec[(b + 1) & 1][0], rec + off, nb * uint32_t(sizeof(Rec)), &s_full[(b + 1) & 1]);
+      bulk_g2s(&s_cull[(b + 1) & 1][0], cull + off, nb * uint32_t(sizeof(float4)), &s_full[(b + 1) & 1]);
     }
     mbar_wait(&s_full[b & 1], (b >> 1) & 1);
     const Rec* batch = s_rec[b & 1];
+    const float4* boxes = s_cull[b & 1];
     const int n = min(BATCH, todo);
-    for (int j = 0; !done && j < n; ++j) {
-      contributor++;
-      const float4 a = *reinterpret_cast<const float4*>(&batch[j].x);    // x y ca cb
-      const float2 c2 = *reinterpret_cast<const float2*>(&batch[j].cc);  // cc o
-      const float dx = __fsub_rn(a.x, pxf), dy = __fsub_rn(a.y, pyf);
-      const float power = gauss_power(a.z, a.w, c2.x, dx, dy);
-      if (power > 0.0f) continue;
-      const float alpha = fminf(0.99f, __fmul_rn(c2.y, expf(power)));
-      if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
-      if (test_T < 0.0001f) { done = true; continue; }
-      const float2 ci = *reinterpret_cast<const float2*>(&batch[j].col);  // col invd
-      C = __fmaf_rn(__fmul_rn(ci.x, alpha), T, C);
-      invd_acc = __fmaf_rn(__fmul_rn(ci.y, alpha), T, invd_acc);
-      if (GEO) {
-        const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
-        M0 = __fmaf_rn(__fmul_rn(mp.x, alpha), T, M0);
-        M1 = __fmaf_rn(__fmul_rn(mp.y, alpha), T, M1);
-        M2 = __fmaf_rn(__fmul_rn(mp.z, alpha), T, M2);
-        M3v = __fmaf_rn(__fmul_rn(mp.w, alpha), T, M3v);
+    const uint32_t pos0 = uint32_t(b) * BATCH;
+    for (int r = 0; r < n; r += 32) {
+      if (__all_sync(0xffffffffu, done)) break;
+      const int idx = r + int(lane);
+      bool cand = false;
+      if (idx < n) {
+        const float4 c = boxes[idx];
+        cand = !(c.x + c.z < bx0 || c.x - c.z > bx1 || c.y + c.w < by0 || c.y - c.w > by1);
       }
-      T = test_T;
-      last_contributor = contributor;
+      uint32_t mask = __ballot_sync(0xffffffffu, cand);
+      while (mask) {
+        const int j = r + __ffs(int(mask)) - 1;
+        mask &= mask - 1;
+        if (!done) {
+          const float4 a = *reinterpret_cast<const float4*>(&batch[j].x);    // x y ca cb
+          const float2 c2 = *reinterpret_cast<const float2*>(&batch[j].cc);  // cc o
+          const float dx = __fsub_rn(a.x, pxf), dy = __fsub_rn(a.y, pyf);
+          const float power = gauss_power(a.z, a.w, c2.x, dx, dy);
+          if (!(power > 0.0f)) {
+            const float alpha = fminf(0.99f, __fmul_rn(c2.y, expf(power)));
+            if (!(alpha < 1.0f / 255.0f)) {
+              const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+              if (test_T < 0.0001f) {
+                done = true;
+              } else {
+                const float2 ci = *reinterpret_cast<const float2*>(&batch[j].col);  // col invd
+                C = __fmaf_rn(__fmul_rn(ci.x, alpha), T, C);
+                invd_acc = __fmaf_rn(__fmul_rn(ci.y, alpha), T, invd_acc);
+                if (GEO) {
+                  const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
+                  M0 = __fmaf_rn(__fmul_rn(mp.x, alpha), T, M0);
+                  M1 = __fmaf_rn(__fmul_rn(mp.y, alpha), T, M1);
+                  M2 = __fmaf_rn(__fmul_rn(mp.z, alpha), T, M2);
+                  M3v = __fmaf_rn(__fmul_rn(mp.w, alpha), T, M3v);
+                }
+                T = test_T;
+                last_contributor = pos0 + uint32_t(j) + 1u;
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -354,7 +435,7 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, 
   }
   uint32_t mc = inside ? last_contributor : 0u;
   mc = __reduce_max_sync(0xffffffffu, mc);
-  if ((tid & 31) == 0) atomicMax(&s_maxc, mc);
+  if (lane == 0) atomicMax(&s_maxc, mc);
   __syncthreads();
   if (tid == 0) tile_maxc[tile] = s_maxc;
 }
@@ -400,40 +481,68 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
   const int W = s->image_width, H = s->image_height;
   ImgState im = ImgState::carve(img, W, H, nullptr);
   BinKeep bk = BinKeep::carve(bin_keep, R, nullptr);
-  BinScratch bs = BinScratch::carve(bin_scratch, R, nullptr);
+  BinScratch bs = BinScratch::carve(bin_scratch, P, R, nullptr);
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   const int64_t nblk = (P + 255) / 256;
   const size_t tiles = size_t(gx) * gy;
 
   CG_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), st));
   if (R > 0) {
-    { StageTimer t_(ST_EMIT_KEYS, st, 1);
-    emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, gx, bs.keys[0], bs.vals[0]); }
-    CG_LAUNCH_CHECK(s->debug, st);
-    int cur = 0;
-    const int end_bit = 32 + int(tile_key_bits(uint32_t(tiles)));
     int rc;
+    // 1. Gaussians by depth (P pairs, 4 digit passes over 8 B pairs)
+    int gcur = 0;
+    { StageTimer t_(ST_SORT, st, 1);
+    init_depth_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, bs.gs.keys[0], bs.gs.vals[0]);
+    CG_LAUNCH_CHECK(s->debug, st);
+    rc = radix_sort_pairs<uint32_t>(bs.gs, P, 32, &gcur, s->debug != 0, st); }
+    if (rc != CG_OK) return rc;
+    const uint32_t* perm = bs.gs.vals[gcur];
+    // 2. offsets in depth order, then one (tile, Gaussian) pair per overlapped tile
+    { StageTimer t_(ST_SCAN, st, 2);
+    perm_block_sums<<<unsigned(nblk), 256, 0, st>>>(P, perm, g);
+    scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
+    CG_LAUNCH_CHECK(s->debug, st);
+    { StageTimer t_(ST_EMIT_KEYS, st, 1);
+    emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, perm, g, gx, bs.is.keys[0], bs.is.vals[0]); }
+    CG_LAUNCH_CHECK(s->debug, st);
+    // 3. stable sort by tile only
+    int cur = 0;
+    const int end_bit = int(tile_key_bits(uint32_t(tiles)));
     { StageTimer t_(ST_SORT, st, 0);
-    rc = radix_sort_pairs(bs, R, end_bit, &cur, s->debug != 0, st); }
+    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st); }
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned((R + 255) / 256);
     { StageTimer t_(ST_TILE_RANGES, st, 1);
-    tile_ranges<<<rb, 256, 0, st>>>(R, bs.keys[cur], im.ranges); }
+    tile_ranges<<<rb, 256, 0, st>>>(R, bs.is.keys[cur], im.ranges); }
     CG_LAUNCH_CHECK(s->debug, st);
     { StageTimer t_(ST_GATHER, st, 1);
-    gather_records<<<rb, 256, 0, st>>>(R, bs.vals[cur], g, colors, s->render_geo ? all_map : nullptr, bk.rec,
-                                       bk.point_list); }
+    gather_records<<<rb, 256, 0, st>>>(R, bs.is.vals[cur], g, colors, s->render_geo ? all_map : nullptr, bk.rec,
+                                       bk.point_list, bk.cull); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
-  dim3 grid(gx, gy), block(TILE_X, TILE_Y);
+  dim3 grid(gx, gy), block(TILE_PIX);
   StageTimer t_blend(ST_BLEND_FWD, st, 1);
   if (s->render_geo)
-    blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map, im.final_T,
-                                            im.n_contrib, im.tile_maxc);
+    blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, bk.rec, bk.cull, W, H, s->bg, out_color, out_invd, out_map,
+                                            im.final_T, im.n_contrib, im.tile_maxc);
   else
-    blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map, im.final_T,
-                                             im.n_contrib, im.tile_maxc);
+    blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, bk.rec, bk.cull, W, H, s->bg, out_color, out_invd, out_map,
+                                             im.final_T, im.n_contrib, im.tile_maxc);
   CG_LAUNCH_CHECK(s->debug, st);
+  return CG_OK;
+}
+
+int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, const void* bin_keep,
+                        const void* bin_scratch, uint64_t* dst, cudaStream_t st) {
+  if (R <= 0) return CG_OK;
+  GeomState g = GeomState::carve(const_cast<void*>(geom), P, nullptr);
+  BinKeep bk = BinKeep::carve(const_cast<void*>(bin_keep), R, nullptr);
+  BinScratch bs = BinScratch::carve(const_cast<void*>(bin_scratch), P, R, nullptr);
+  const size_t tiles = size_t((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  const int passes = min(4, max(1, (int(tile_key_bits(uint32_t(tiles))) + 7) / 8));
+  count_launches(1);
+  rebuild_keys<<<unsigned((R + 255) / 256), 256, 0, st>>>(R, bs.is.keys[passes & 1], bk.point_list, g.depth, dst);
+  CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }
 

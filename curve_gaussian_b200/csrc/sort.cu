@@ -1,14 +1,16 @@
-// Stable LSD radix sort of (uint64 key, uint32 value) pairs, 8 bits per pass,
+// Stable LSD radix sort of (uint32/uint64 key, uint32 value) pairs, 8 bits per pass,
 // single-pass-per-digit ("onesweep") with decoupled look-back.
 //
 // Replaces cub::DeviceRadixSort::SortPairs in the reference binning step
-// (rasterizer_impl.cu:309-314). The sort must be STABLE: equal (tile, depth)
-// keys keep emission order (ascending Gaussian index), which is what makes
-// point_list bit-exact against the reference.
+// (rasterizer_impl.cu:309-314) and in simple-knn (simple_knn.cu:207-214). The sort
+// must be STABLE: equal keys keep their input order, which is what makes point_list
+// bit-exact against the reference (see BinScratch in common.cuh for how the binning
+// step splits the reference's one 64-bit sort into a per-Gaussian depth sort and a
+// per-instance tile sort with the same result).
 //
-// HBM traffic: one 8 B/key histogram pass + per digit pass 12 B read + 12 B
-// write; digit passes whose histogram shows a single occupied bin are still
-// run (ping-pong parity stays fixed), they stream at copy speed.
+// HBM traffic: one histogram pass over the keys + per digit pass one read and one
+// write of every pair; digit passes whose histogram shows a single occupied bin are
+// still run (ping-pong parity stays fixed), they stream at copy speed.
 #include "common.cuh"
 
 namespace cg {
@@ -20,15 +22,16 @@ constexpr uint32_t VALUE_MASK = (1u << FLAG_SHIFT) - 1u;
 constexpr uint32_t FLAG_AGG = 1u;   // tile-local count published
 constexpr uint32_t FLAG_INC = 2u;   // inclusive prefix published
 
+template <typename K>
 __global__ void __launch_bounds__(256)
-sort_histogram(const uint64_t* __restrict__ keys, int64_t R, int passes, uint32_t* __restrict__ hist) {
+sort_histogram(const K* __restrict__ keys, int64_t R, int passes, uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
   for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < R; i += stride) {
-    uint64_t k = keys[i];
-    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + ((k >> (8 * p)) & 255u)], 1u);
+    K k = keys[i];
+    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + uint32_t((k >> (8 * p)) & 255u)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
@@ -55,8 +58,9 @@ __global__ void __launch_bounds__(256) sort_scan_bins(uint32_t* __restrict__ his
   h[threadIdx.x] = base + inc - v;
 }
 
+template <typename K>
 struct SortSmem {
-  uint64_t keys[SORT_TILE];
+  K keys[SORT_TILE];
   uint32_t vals[SORT_TILE];
   uint32_t whist[SORT_THREADS / 32][257];  // per-warp digit counters (+1 bin for tail padding)
   uint32_t local_start[256];
@@ -64,13 +68,14 @@ struct SortSmem {
   uint32_t tile_id;
 };
 
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                   uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+template <typename K>
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 4 ? 3 : 2)
+sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                   K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                    int64_t R, int shift, const uint32_t* __restrict__ digit_base,
                    uint32_t* __restrict__ ticket, uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortSmem& s = *reinterpret_cast<SortSmem*>(smem_raw);
+  SortSmem<K>& s = *reinterpret_cast<SortSmem<K>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = SORT_THREADS / 32;
 
@@ -82,14 +87,14 @@ sort_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restr
   const int64_t tile_base = int64_t(tile) * SORT_TILE;
   const int64_t warp_base = tile_base + int64_t(warp) * (32 * SORT_ITEMS);
 
-  uint64_t k[SORT_ITEMS];
+  K k[SORT_ITEMS];
   uint32_t v[SORT_ITEMS];
   uint16_t rank[SORT_ITEMS];
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
     int64_t idx = warp_base + i * 32 + lane;
     bool ok = idx < R;
-    k[i] = ok ? keys_in[idx] : ~0ull;
+    k[i] = ok ? keys_in[idx] : K(~K(0));
     v[i] = ok ? vals_in[idx] : 0u;
   }
 
@@ -177,7 +182,7 @@ sort_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restr
   int64_t rem = R - tile_base;
   const int count = rem < SORT_TILE ? int(rem) : SORT_TILE;
   for (int j = tid; j < count; j += SORT_THREADS) {
-    uint64_t key = s.keys[j];
+    K key = s.keys[j];
     uint32_t d = uint32_t((key >> shift) & 255u);
     int64_t g = int64_t(s.gbase[d]) + j;
     keys_out[g] = key;
@@ -187,24 +192,23 @@ sort_onesweep_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restr
 
 }  // namespace
 
-// Sorts b.keys[0]/b.vals[0] on bits [0,end_bit). *out_buf tells which of the
-// two ping-pong buffers holds the result.
-int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
-                     bool debug, cudaStream_t stream) {
+template <typename K>
+int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf, bool debug, cudaStream_t stream) {
   *out_buf = 0;
   if (R <= 0) return CG_OK;
   if (R >= (int64_t(1) << FLAG_SHIFT)) {
-    set_error("radix sort: %lld instances exceed the 2^30 look-back word", (long long)R);
+    set_error("radix sort: %lld pairs exceed the 2^30 look-back word", (long long)R);
     return CG_ERR_CAPACITY;
   }
   int passes = (end_bit + 7) / 8;
-  if (passes > SORT_MAX_PASSES) passes = SORT_MAX_PASSES;
+  if (passes > int(sizeof(K))) passes = int(sizeof(K));
+  if (passes < 1) passes = 1;
   const int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
 
   static bool attr_set = false;
   if (!attr_set) {
-    CG_CUDA(cudaFuncSetAttribute(sort_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 int(sizeof(SortSmem))));
+    CG_CUDA(cudaFuncSetAttribute(sort_onesweep_pass<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(sizeof(SortSmem<K>))));
     attr_set = true;
   }
   CG_CUDA(cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * SORT_MAX_PASSES * 256, stream));
@@ -213,14 +217,14 @@ int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
 
   int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
   count_launches(2 + passes);
-  sort_histogram<<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist);
+  sort_histogram<K><<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
   sort_scan_bins<<<passes, 256, 0, stream>>>(b.hist);
   CG_LAUNCH_CHECK(debug, stream);
 
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
-    sort_onesweep_pass<<<unsigned(ntiles), SORT_THREADS, sizeof(SortSmem), stream>>>(
+    sort_onesweep_pass<K><<<unsigned(ntiles), SORT_THREADS, sizeof(SortSmem<K>), stream>>>(
         b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, 8 * p,
         b.hist + p * 256, b.ticket + p, b.status + size_t(p) * ntiles * 256);
     CG_LAUNCH_CHECK(debug, stream);
@@ -229,5 +233,8 @@ int radix_sort_pairs(const BinScratch& b, int64_t R, int end_bit, int* out_buf,
   *out_buf = cur;
   return CG_OK;
 }
+
+template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t);
+template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t);
 
 }  // namespace cg

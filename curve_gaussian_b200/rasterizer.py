@@ -115,7 +115,7 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
                                           geom.numel(), C.byref(R), stream), "cg_raster_fwd_geom")
         R = int(R.value)
         bin_keep = _bytes(lib.cg_raster_bin_keep_bytes(R), dev)
-        bin_scratch = _bytes(lib.cg_raster_bin_scratch_bytes(R), dev)
+        bin_scratch = _bytes(lib.cg_raster_bin_scratch_bytes(P, R), dev)
         _lib.check(lib.cg_raster_fwd_blend(C.byref(s), P, R, _lib.ptr(colors), _lib.ptr(amap), geom.data_ptr(),
                                            img.data_ptr(), bin_keep.data_ptr(), bin_scratch.data_ptr(),
                                            color.data_ptr(), invdepth.data_ptr(), out_all_map.data_ptr(), stream),

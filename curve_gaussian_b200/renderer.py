@@ -7,7 +7,60 @@ import math
 import torch
 
 from .activation import curve_activate
+from .loss import rotate_channels
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+
+class RenderPackage(dict):
+    """The output dict of render() with the same keys as the reference
+    (gaussian_renderer/__init__.py:147-155). `visibility_filter` (a host-synchronising
+    nonzero()) and `rend_dir` (a per-pixel rotation nothing in train.py's loss reads) are
+    produced on first access instead of on every call; every other access pattern of a
+    dict (in, keys(), items(), len, iteration, get) sees them as present."""
+
+    def __init__(self, eager, lazy):
+        super().__init__(eager)
+        self._lazy = dict(lazy)
+
+    def _force(self, key):
+        fn = self._lazy.pop(key, None)
+        if fn is not None:
+            super().__setitem__(key, fn())
+
+    def _force_all(self):
+        for k in list(self._lazy):
+            self._force(k)
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            self._force(key)
+            return super().__getitem__(key)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return super().__contains__(key) or key in self._lazy
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __len__(self):
+        return super().__len__() + len(self._lazy)
+
+    def __iter__(self):
+        self._force_all()
+        return super().__iter__()
+
+    def keys(self):
+        self._force_all()
+        return super().keys()
+
+    def values(self):
+        self._force_all()
+        return super().values()
+
+    def items(self):
+        self._force_all()
+        return super().items()
 
 
 def _can_fuse(pc) -> bool:
@@ -82,15 +135,16 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
     rendered_image = rendered_image.clamp(0, 1)
     rendered_alpha = out_all_map[3:4, ]
-    rendered_dir = out_all_map[0:3]
-    rendered_dir = (rendered_dir.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
+    wvt = viewpoint_camera.world_view_transform
 
-    return {
+    return RenderPackage({
         "render": rendered_image,
         "viewspace_points": screenspace_points,
-        "visibility_filter": (radii > 0).nonzero(),
         "radii": radii,
         "depth": depth_image,
-        "rend_dir": rendered_dir,
         "rend_alpha": rendered_alpha,
-    }
+    }, {
+        "visibility_filter": lambda: (radii > 0).nonzero(),
+        # (dir.permute(1,2,0) @ wvt[:3,:3].T).permute(2,0,1) as one per-pixel kernel
+        "rend_dir": lambda: rotate_channels(out_all_map[0:3], wvt[:3, :3]),
+    })

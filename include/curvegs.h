@@ -77,11 +77,12 @@ typedef struct cg_raster_settings {
 /* Sizes of the opaque state buffers the caller must allocate (bytes).
  * geom: per-Gaussian state, img: per-pixel/per-tile state, both saved for
  * backward. bin_keep: sorted per-instance records + point list, saved for
- * backward. bin_scratch: sort double buffers, only live during forward. */
+ * backward. bin_scratch: sort double buffers (P Gaussians by depth, R instances
+ * by tile), only live during forward. */
 size_t cg_raster_geom_bytes(int64_t P);
 size_t cg_raster_img_bytes(int32_t W, int32_t H);
 size_t cg_raster_bin_keep_bytes(int64_t R);
-size_t cg_raster_bin_scratch_bytes(int64_t R);
+size_t cg_raster_bin_scratch_bytes(int64_t P, int64_t R);
 
 /* Forward, stage 1: per-Gaussian EWA projection + tile counts + prefix scan.
  * Writes radii[P] (int32) and the geom state; returns the number of
@@ -99,8 +100,9 @@ int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P,
                        int64_t* num_rendered,     /* out, host */
                        void* stream);
 
-/* Forward, stage 2: duplicate -> stable radix sort -> tile ranges -> record
- * gather -> per-tile front-to-back blend. colors is (P,1); all_map is (P,4)
+/* Forward, stage 2: depth-sort the Gaussians -> duplicate per tile -> stable radix
+ * sort by tile (same permutation as the reference's 64-bit tile|depth sort) -> tile
+ * ranges -> record gather -> per-tile front-to-back blend. colors is (P,1); all_map is (P,4)
  * or NULL when !render_geo. Outputs are (1,H,W), (1,H,W), (4,H,W). */
 int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R,
                         const float* colors, const float* all_map,
@@ -199,6 +201,35 @@ int cg_ssim_bwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
                 const float* img1, const float* img2, const float* dL_dmap,
                 const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
                 float* dL_dimg1, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Fused image loss of the training step (reference caller: train.py)   */
+/* ------------------------------------------------------------------ */
+
+/* loss = lambda_mse * ((1 - lambda_dssim) * edge_aware_loss(img, gt, threshold)
+ *                      + lambda_dssim * (1 - mean(ssim_map(img, gt))))
+ * for single-channel (H,W) images: train.py:101-107 with utils/loss_utils.py:94-115
+ * (class-balanced weighted MSE) and fused_ssim (fused-ssim/ssim.cu:187-366) in ONE
+ * forward and ONE backward kernel. loss_out is a DEVICE scalar (no host sync). stats
+ * is cg_edge_ssim_loss_stats_bytes() of device memory kept for the backward together
+ * with the three partial maps. g_loss is the DEVICE upstream scalar (NULL = 1). */
+size_t cg_edge_ssim_loss_stats_bytes(void);
+int cg_edge_ssim_loss_fwd(int32_t H, int32_t W, const float* img, const float* gt,
+                          float threshold, float lambda_mse, float lambda_dssim, float C1, float C2,
+                          void* stats, float* loss_out,
+                          float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* stream);
+int cg_edge_ssim_loss_bwd(int32_t H, int32_t W, const float* img, const float* gt,
+                          float threshold, float lambda_mse, float lambda_dssim,
+                          const void* stats, const float* g_loss,
+                          const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
+                          float* dL_dimg, void* stream);
+
+/* out[c][i] = sum_k in[k][i] * M[c][k] over n pixels of a (3,n) planar image; M is a
+ * DEVICE 3x3 with row stride ld floats (transpose != 0 applies M^T). This is the
+ * view->world rotation of the direction channels in render()
+ * (gaussian_renderer/__init__.py:144), a (H*W,3)x(3,3) GEMM in the reference. */
+int cg_rotate_channels(int64_t n, const float* in, const float* m3x3, int32_t ld, int32_t transpose,
+                       float* out, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* simple-knn (reference: submodules/simple-knn)                        */

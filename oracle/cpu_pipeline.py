@@ -106,3 +106,17 @@ def cpu_train_step(curve_points, width, opacity_logit, mask_logit, is_bezier, n,
     t4 = time.perf_counter()
     timing.update(sample_s=t1 - t0, raster_fwd_s=t2 - t1, loss_s=t3 - t2, backward_s=t4 - t3, total_s=t4 - t0)
     return float(loss), dict(curve_points=cp.grad, width=w.grad, opacity=ol.grad), timing
+
+
+def edge_ssim_loss_ref(image, gt, threshold=0.1, lambda_mse=10.0, lambda_dssim=0.1):
+    """CPU restatement of train.py:101-107 for a (1,H,W) image: returns (loss, dL/dimage).
+    edge_aware_loss is the torch expression above; SSIM value and gradient come from the C oracle
+    (fused-ssim/ssim.cu:187-366 restated in oracle/ssim_oracle.c)."""
+    img = image.detach().clone().float().requires_grad_(True)
+    Ll1 = edge_aware_loss(img, gt, threshold)
+    m, d1, d2, d3 = O.ssim_fwd(img[None].detach().numpy(), gt[None].numpy())
+    loss = lambda_mse * ((1.0 - lambda_dssim) * float(Ll1) + lambda_dssim * (1.0 - float(m.mean())))
+    g_l1 = torch.autograd.grad(lambda_mse * (1.0 - lambda_dssim) * Ll1, img)[0]
+    g_ssim = O.ssim_bwd(img[None].detach().numpy(), gt[None].numpy(), np.full(m.shape, 1.0 / m.size, np.float32),
+                        d1, d2, d3)[0]
+    return loss, g_l1 - lambda_mse * lambda_dssim * torch.from_numpy(g_ssim)

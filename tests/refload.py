@@ -25,7 +25,8 @@ _cache = {}
 
 def ref_rasterizer():
     if "r" not in _cache:
-        _cache["r"] = _load("_C", "diff_cur_rasterization_C.so")
+        # both extensions export PyInit__C; distinct dotted names keep CPython's extension cache from aliasing them
+        _cache["r"] = _load("ref_diff_cur_rasterization._C", "diff_cur_rasterization_C.so")
     return _cache["r"]
 
 
@@ -37,5 +38,5 @@ def ref_ssim():
 
 def ref_knn():
     if "k" not in _cache:
-        _cache["k"] = _load("_C", "simple_knn_C.so")
+        _cache["k"] = _load("ref_simple_knn._C", "simple_knn_C.so")
     return _cache["k"]
