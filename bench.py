@@ -180,15 +180,43 @@ def run_ours(a):
     flat = fg.flat
     flat_host = torch.empty(flat.shape, dtype=flat.dtype).pin_memory()
 
-    def step(i, host_io):
+    # e2e plumbing: the step's edge map comes from pinned host memory and its loss + flat gradient go back to
+    # pinned host memory EVERY step, inside the timed region; the copies run on side streams (double-buffered)
+    # so they overlap the kernels of the neighbouring steps, and the host reads the results at the end.
+    h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    gt_buf = [torch.empty_like(gts_dev[0]) for _ in range(2)]
+    gt_ready = [torch.cuda.Event() for _ in range(2)]
+    gt_free = [torch.cuda.Event() for _ in range(2)]
+    flat_host2 = [flat_host, torch.empty_like(flat_host).pin_memory()]
+    out_free = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(4096, dtype=torch.float32).pin_memory()
+    flat_out = [torch.empty_like(flat) for _ in range(2)]
+
+    from curve_gaussian_b200 import rasterizer as rz
+    R_seen = []
+
+    def prefetch(i):
+        k = i % 2
+        with torch.cuda.stream(h2d):
+            h2d.wait_event(gt_free[k])          # the step that last used this buffer is done with it
+            gt_buf[k].copy_(gts_host[i % len(cams)], non_blocking=True)
+            gt_ready[k].record(h2d)
+
+    def step(i, host_io, first=False):
         cam = cams[i % len(cams)]
+        main = torch.cuda.current_stream(dev)
         flat.zero_()
         if host_io:
-            gt = gts_host[i % len(cams)].to(dev, non_blocking=True)
+            if first:
+                prefetch(i)
+            main.wait_event(gt_ready[i % 2])
+            gt = gt_buf[i % 2]
+            prefetch(i + 1)
         else:
             gt = gts_dev[i % len(cams)]
         model.prepare_scaling_rot()
         image = render(cam, model, pipe, bg)["render"]
+        R_seen.append(rz.rasterize_forward_raw.last_R)
         if a.unfused_loss:
             Ll1 = edge_aware_loss(image, gt)
             ssim_value = fused_ssim(image.unsqueeze(0), gt.unsqueeze(0))
@@ -199,13 +227,24 @@ def run_ours(a):
         loss.backward()
         fg.all_reduce()
         if host_io:
-            flat_host.copy_(flat, non_blocking=True)
-            return loss.item()
+            k = i % 2
+            gt_free[k].record(main)
+            main.wait_event(out_free[k])        # previous D2H out of this staging buffer finished
+            flat_out[k].copy_(flat)             # snapshot: the next step zeroes `flat` while the copy is in flight
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                flat_host2[k].copy_(flat_out[k], non_blocking=True)
+                loss_host[i % loss_host.numel()].copy_(loss.detach(), non_blocking=True)
+                out_free[k].record(d2h)
         return loss
 
     def timed(host_io, steps, warmup, profile=False):
+        for ev in gt_free + out_free:
+            ev.record(torch.cuda.current_stream(dev))
         for i in range(warmup):
-            step(i, host_io)
+            step(i, host_io, first=(i == 0))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -216,7 +255,10 @@ def run_ours(a):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            step(warmup + i, host_io)
+            step(warmup + i, host_io, first=(i == 0 and warmup == 0))
+        if host_io:
+            torch.cuda.current_stream(dev).wait_stream(d2h)   # every step's loss + gradient has reached the host
+            torch.cuda.current_stream(dev).wait_stream(h2d)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -233,23 +275,26 @@ def run_ours(a):
     W_, K = max(a.warmup, 3), a.steps
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches = timed(False, K, W_, profile=True)
+    ms, launches = timed(False, K, W_)
     clocks = sampler.stop()
-    stages = _lib.profile_read()
     ms_e2e, _ = timed(True, K, W_)
+    # per-stage kernel times come from a separate short pass: the CUDA events the library records around
+    # every stage cost a few us each, which the headline numbers above should not carry
+    ms_prof, _ = timed(False, min(K, 10), 1, profile=True)
+    stages = _lib.profile_read()
+    ms_prof_step = ms_prof / min(K, 10)
 
     views = K * world
     value = views / (ms / 1e3)
     e2e_value = views / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel (HBM-bound accounting, SURVEY 8d / DESIGN.md)
-    with torch.no_grad():
-        pk = render(cams[0], model, pipe, bg)
     P = B * n
     Npix = W * H
-    from curve_gaussian_b200 import rasterizer as rz
-    R = getattr(rz.rasterize_forward_raw, "last_R", None)
-    per_stage = {k: v[0] / v[1] for k, v in stages.items()}
+    last = R_seen[-min(K, 10):]                    # the views of the profiled pass
+    R = int(sum(last) / max(len(last), 1))         # mean tile-instances per view there
+    per_stage = {k: v[0] / v[1] for k, v in stages.items()}          # ms per launch of the stage
+    per_stage_step = {k: v[0] / min(K, 10) for k, v in stages.items()}  # ms per step (a stage may run twice)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -260,8 +305,11 @@ def run_ours(a):
     alg_bytes = {
         "blend_bwd": 52 * (R or 0) + 32 * Npix + 48 * P,
         "blend_fwd": 52 * (R or 0) + 32 * Npix,
-        "radix_sort": (8 + 6 * 24) * (R or 0),
-        "gather_records": (4 + 48 + 48 + 4) * (R or 0),
+        # depth sort of the P Gaussians (histogram read + 4 passes of 8-byte pairs r+w) and tile sort of the
+        # R instances (histogram read + 2 passes of 8-byte pairs r+w); radix_sort is timed per launch, so use R's
+        "radix_sort": (4 + 2 * 16) * (R or 0),
+        # read (tile, id) 8 + gathered attributes 48, write record 48 + id 4 + cull box 16
+        "gather_records": (8 + 48 + 68) * (R or 0),
         "preprocess_fwd": (44 + 36) * P,
         "preprocess_bwd": (76 + 40) * P,
     }
@@ -277,7 +325,7 @@ def run_ours(a):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms": round(per_stage[dom], 4), "algorithmic_bytes": alg_bytes[dom],
-                    "share_of_step": round(stages[dom][0] / ms, 3)}
+                    "share_of_step": round(per_stage_step[dom] / ms_prof_step, 3)}
     bytes_view = 264 * P + 148 * (R or 0) + 64 * Npix + 88 * P + 20 * Npix
     e2e_frac = bytes_view * value / 1e9 / peak
 
@@ -291,7 +339,8 @@ def run_ours(a):
                    "d2h_bytes_per_step": int(flat.numel() * 4 + 4)},
            "gpu_launches": int(launches),
            "roofline": roofline,
-           "stage_ms": {k: round(v, 4) for k, v in sorted(per_stage.items(), key=lambda kv: -kv[1])},
+           "stage_ms": {k: round(v, 4) for k, v in sorted(per_stage_step.items(), key=lambda kv: -kv[1])},
+           "stage_ms_note": "ms per step per stage, CUDA events on the launch stream, from a separate profiled pass",
            "hbm_algorithmic": {"bytes_per_view": bytes_view, "achieved_GBps": round(bytes_view * value / 1e9 / world, 1),
                                "frac_of_peak_per_gpu": round(e2e_frac / world, 4)}}
 

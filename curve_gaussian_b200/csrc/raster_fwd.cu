@@ -189,10 +189,17 @@ perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
 // One (tile, Gaussian) pair per overlapped tile, row-major over the rect like
 // rasterizer_impl.cu:70-111, but Gaussians are visited in depth order and the key is the
 // tile index alone (see BinScratch). Slot i of the scan is Gaussian perm[i].
+// The reference walks each rect serially in one thread; here a CTA scans its 256 tile
+// counts into shared memory and then every thread produces output slots tid, tid+256, ...
+// (binary search of the slot in the scanned counts), so the writes are coalesced and the
+// work is balanced no matter how uneven the rects are.
 __global__ void __launch_bounds__(256)
 emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x, uint32_t* __restrict__ keys,
           uint32_t* __restrict__ vals) {
   __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_off[257];
+  __shared__ uint32_t s_idx[256];
+  __shared__ uint2 s_rect[256];
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t idx = (i < P) ? perm[i] : 0u;
@@ -203,31 +210,32 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
     if (lane >= o) inc += n;
   }
   if (lane == 31) s_w[w] = inc;
+  s_idx[threadIdx.x] = idx;
+  if (cnt) s_rect[threadIdx.x] = g.rect[idx];
   __syncthreads();
-  uint32_t off = g.blk_prefix[blockIdx.x] + inc - cnt;
-  for (uint32_t k = 0; k < w; ++k) off += s_w[k];
-  if (cnt == 0) return;
-  const uint2 rc = g.rect[idx];
-  const uint32_t mnx = rc.x & 0xffffu, mny = rc.x >> 16, mxx = rc.y & 0xffffu, mxy = rc.y >> 16;
-  for (uint32_t y = mny; y < mxy; ++y)
-    for (uint32_t x = mnx; x < mxx; ++x) {
-      keys[off] = y * uint32_t(grid_x) + x;
-      vals[off] = idx;
-      ++off;
+  uint32_t wb = 0;
+  for (uint32_t k = 0; k < w; ++k) wb += s_w[k];
+  s_off[threadIdx.x] = wb + inc - cnt;
+  if (threadIdx.x == 255) s_off[256] = wb + inc;
+  __syncthreads();
+  const uint32_t total = s_off[256];
+  const uint32_t base = g.blk_prefix[blockIdx.x];
+  for (uint32_t o = threadIdx.x; o < total; o += 256) {
+    // last t with s_off[t] <= o; among equal offsets that is the one with a non-zero count
+    uint32_t lo = 0, hi = 256;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_off[mid] <= o) lo = mid; else hi = mid;
     }
-}
-
-__global__ void __launch_bounds__(256)
-tile_ranges(int64_t R, const uint32_t* __restrict__ tiles_sorted, uint2* __restrict__ ranges) {
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= R) return;
-  const uint32_t cur = tiles_sorted[i];
-  if (i == 0) ranges[cur].x = 0;
-  else {
-    const uint32_t prev = tiles_sorted[i - 1];
-    if (cur != prev) { ranges[prev].y = uint32_t(i); ranges[cur].x = uint32_t(i); }
+    const uint32_t local = o - s_off[lo];
+    const uint2 rc = s_rect[lo];
+    const uint32_t mnx = rc.x & 0xffffu, mny = rc.x >> 16, mxx = rc.y & 0xffffu;
+    const uint32_t wdt = mxx - mnx;
+    const uint32_t ry = local / wdt, rx = local - ry * wdt;
+    keys[base + o] = (mny + ry) * uint32_t(grid_x) + (mnx + rx);
+    vals[base + o] = s_idx[lo];
   }
-  if (i == R - 1) ranges[cur].y = uint32_t(R);
 }
 
 // The reference's 64-bit sort keys, rebuilt for parity checks: tile<<32 | float_bits(depth).
@@ -239,7 +247,7 @@ rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_
   keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
 }
 
-// Sorted instance i -> contiguous 48-byte record + point list entry + cull box.
+// Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry + cull box.
 //
 // The cull box {x, y, hx, hy} bounds, conservatively, the pixels this instance can
 // contribute to. A pixel contributes only if alpha = min(0.99, o*exp(power)) >= 1/255
@@ -249,11 +257,22 @@ rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_
 // `power`, and degenerate inputs (NaN, non-positive-definite conic) get an infinite box, so
 // skipping an instance whose box misses a warp's pixel block never changes a result bit.
 __global__ void __launch_bounds__(256)
-gather_records(int64_t R, const uint32_t* __restrict__ sorted_vals, GeomState g,
-               const float* __restrict__ colors, const float* __restrict__ all_map,
-               Rec* __restrict__ rec, uint32_t* __restrict__ point_list, float4* __restrict__ cull) {
+gather_records(int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint32_t* __restrict__ sorted_vals,
+               GeomState g, const float* __restrict__ colors, const float* __restrict__ all_map,
+               uint2* __restrict__ ranges, Rec* __restrict__ rec, uint32_t* __restrict__ point_list,
+               float4* __restrict__ cull) {
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
+  {
+    // per-tile [start, end) into the sorted list (rasterizer_impl.cu:116-138); ranges is zero-filled
+    const uint32_t cur = sorted_tiles[i];
+    if (i == 0) ranges[cur].x = 0;
+    else {
+      const uint32_t prev = sorted_tiles[i - 1];
+      if (cur != prev) { ranges[prev].y = uint32_t(i); ranges[cur].x = uint32_t(i); }
+    }
+    if (i == R - 1) ranges[cur].y = uint32_t(R);
+  }
   const uint32_t id = sorted_vals[i];
   point_list[i] = id;
   const float2 xy = g.xy[id];
@@ -512,12 +531,9 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st); }
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned((R + 255) / 256);
-    { StageTimer t_(ST_TILE_RANGES, st, 1);
-    tile_ranges<<<rb, 256, 0, st>>>(R, bs.is.keys[cur], im.ranges); }
-    CG_LAUNCH_CHECK(s->debug, st);
     { StageTimer t_(ST_GATHER, st, 1);
-    gather_records<<<rb, 256, 0, st>>>(R, bs.is.vals[cur], g, colors, s->render_geo ? all_map : nullptr, bk.rec,
-                                       bk.point_list, bk.cull); }
+    gather_records<<<rb, 256, 0, st>>>(R, bs.is.keys[cur], bs.is.vals[cur], g, colors,
+                                       s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list, bk.cull); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   dim3 grid(gx, gy), block(TILE_PIX);

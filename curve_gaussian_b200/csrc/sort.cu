@@ -24,14 +24,14 @@ constexpr uint32_t FLAG_INC = 2u;   // inclusive prefix published
 
 template <typename K>
 __global__ void __launch_bounds__(256)
-sort_histogram(const K* __restrict__ keys, int64_t R, int passes, uint32_t* __restrict__ hist) {
+sort_histogram(const K* __restrict__ keys, int64_t R, int passes, int bpp, uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
   for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < R; i += stride) {
     K k = keys[i];
-    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + uint32_t((k >> (8 * p)) & 255u)], 1u);
+    for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + (uint32_t(k >> (bpp * p)) & ((1u << bpp) - 1u))], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
@@ -72,7 +72,7 @@ template <typename K>
 __global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 4 ? 3 : 2)
 sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                   int64_t R, int shift, const uint32_t* __restrict__ digit_base,
+                   int64_t R, int shift, uint32_t dmask, const uint32_t* __restrict__ digit_base,
                    uint32_t* __restrict__ ticket, uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SortSmem<K>& s = *reinterpret_cast<SortSmem<K>*>(smem_raw);
@@ -98,23 +98,30 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     v[i] = ok ? vals_in[idx] : 0u;
   }
 
-  // Stable in-warp ranking, item by item (items are in memory order).
+  // Stable in-warp ranking (items are in memory order). For each item the lanes holding the
+  // same digit form a peer group (match.any); the group's first lane bumps the warp's digit
+  // counter with ONE shared-memory atomic that returns the group's base. The atomics of
+  // successive items to the same counter execute in issue order, so nothing here depends on
+  // the previous item through registers: the 16 match/atomic/shuffle chains overlap instead
+  // of forming one 16-deep serial chain.
   uint32_t* wh = s.whist[warp];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    int64_t idx = warp_base + i * 32 + lane;
-    uint32_t d = (idx < R) ? uint32_t((k[i] >> shift) & 255u) : 256u;
-    uint32_t m = __match_any_sync(0xffffffffu, d);
-    uint32_t leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (lane == leader) {
-      base = wh[d];
-      wh[d] = base + __popc(m);
+  for (int h = 0; h < SORT_ITEMS; h += 8) {
+    uint32_t m[8], old[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t idx = warp_base + (h + i) * 32 + lane;
+      const uint32_t d = (idx < R) ? (uint32_t(k[h + i] >> shift) & dmask) : 256u;
+      m[i] = __match_any_sync(0xffffffffu, d);
+      old[i] = 0;
+      if (lane == uint32_t(__ffs(int(m[i])) - 1)) old[i] = atomicAdd(&wh[d], uint32_t(__popc(m[i])));
     }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    rank[i] = uint16_t(base + __popc(m & lt_mask));
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t base = __shfl_sync(0xffffffffu, old[i], __ffs(int(m[i])) - 1);
+      rank[h + i] = uint16_t(base + __popc(m[i] & lt_mask));
+    }
   }
   __syncthreads();
 
@@ -129,10 +136,13 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
       total += c;
     }
     uint32_t* st = status + size_t(tile) * 256 + d;
-    if (tile == 0) {
-      atomicExch(st, (FLAG_INC << FLAG_SHIFT) | total);
-    } else {
-      atomicExch(st, (FLAG_AGG << FLAG_SHIFT) | total);
+    const bool live = d <= dmask;   // bins above the digit width stay empty: no publish, no look-back
+    if (live) {
+      if (tile == 0) {
+        atomicExch(st, (FLAG_INC << FLAG_SHIFT) | total);
+      } else {
+        atomicExch(st, (FLAG_AGG << FLAG_SHIFT) | total);
+      }
     }
     // block-wide exclusive scan of `total` over digits -> local_start
     uint32_t inc = total;
@@ -148,16 +158,35 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     const uint32_t lstart = wb + inc - total;
     s.local_start[d] = lstart;
 
+    // Decoupled look-back, LB predecessors per round trip: all tiles of the first wave publish
+    // their aggregates at about the same time, so a one-at-a-time walk ripples through
+    // ~ntiles/2 dependent L2 round trips; independent loads of a window cut that by LB.
     uint32_t excl = 0;
-    if (tile > 0) {
+    if (tile > 0 && live) {
+      constexpr int LB = 16;
       int64_t t = int64_t(tile) - 1;
-      while (true) {
-        uint32_t w;
-        volatile uint32_t* p = status + size_t(t) * 256 + d;
-        do { w = *p; } while ((w >> FLAG_SHIFT) == 0u);
-        excl += w & VALUE_MASK;
-        if ((w >> FLAG_SHIFT) == FLAG_INC) break;
-        --t;  // tile 0 always publishes FLAG_INC, so t never goes below 0
+      bool done = false;
+      while (!done) {
+        uint32_t w[LB];
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+          const int64_t ti = t - i;
+          w[i] = (ti >= 0) ? *reinterpret_cast<volatile const uint32_t*>(status + size_t(ti) * 256 + d)
+                           : (FLAG_INC << FLAG_SHIFT);   // tile 0 always publishes FLAG_INC; this is never consumed
+        }
+        int used = 0;
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+          if (!done && used == i) {
+            const uint32_t f = w[i] >> FLAG_SHIFT;
+            if (f != 0u) {
+              excl += w[i] & VALUE_MASK;
+              used = i + 1;
+              if (f == FLAG_INC) done = true;
+            }
+          }
+        }
+        t -= used;
       }
       atomicExch(st, (FLAG_INC << FLAG_SHIFT) | ((excl + total) & VALUE_MASK));
     }
@@ -170,7 +199,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
   for (int i = 0; i < SORT_ITEMS; ++i) {
     int64_t idx = warp_base + i * 32 + lane;
     if (idx < R) {
-      uint32_t d = uint32_t((k[i] >> shift) & 255u);
+      uint32_t d = uint32_t(k[i] >> shift) & dmask;
       uint32_t pos = s.local_start[d] + s.whist[warp][d] + rank[i];
       s.keys[pos] = k[i];
       s.vals[pos] = v[i];
@@ -183,7 +212,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
   const int count = rem < SORT_TILE ? int(rem) : SORT_TILE;
   for (int j = tid; j < count; j += SORT_THREADS) {
     K key = s.keys[j];
-    uint32_t d = uint32_t((key >> shift) & 255u);
+    uint32_t d = uint32_t(key >> shift) & dmask;
     int64_t g = int64_t(s.gbase[d]) + j;
     keys_out[g] = key;
     vals_out[g] = s.vals[j];
@@ -200,9 +229,13 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
     set_error("radix sort: %lld pairs exceed the 2^30 look-back word", (long long)R);
     return CG_ERR_CAPACITY;
   }
+  if (end_bit > int(8 * sizeof(K))) end_bit = int(8 * sizeof(K));
   int passes = (end_bit + 7) / 8;
-  if (passes > int(sizeof(K))) passes = int(sizeof(K));
   if (passes < 1) passes = 1;
+  // equal digit widths (e.g. 13 tile bits -> 2 x 7 instead of 8 + 5): fewer bins per pass means
+  // longer runs per bin in the scatter and fewer look-back chains
+  const int bpp = end_bit <= 0 ? 1 : (end_bit + passes - 1) / passes;
+  const uint32_t dmask = (1u << bpp) - 1u;
   const int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
 
   static bool attr_set = false;
@@ -211,13 +244,14 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
                                  int(sizeof(SortSmem<K>))));
     attr_set = true;
   }
-  CG_CUDA(cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * SORT_MAX_PASSES * 256, stream));
-  CG_CUDA(cudaMemsetAsync(b.ticket, 0, sizeof(uint32_t) * 32, stream));
-  CG_CUDA(cudaMemsetAsync(b.status, 0, sizeof(uint32_t) * size_t(passes) * ntiles * 256, stream));
+  // hist, ticket and status are carved back to back: one memset covers all three
+  CG_CUDA(cudaMemsetAsync(b.hist, 0,
+                          size_t(reinterpret_cast<char*>(b.status + size_t(passes) * ntiles * 256) -
+                                 reinterpret_cast<char*>(b.hist)), stream));
 
   int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
   count_launches(2 + passes);
-  sort_histogram<K><<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist);
+  sort_histogram<K><<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, bpp, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
   sort_scan_bins<<<passes, 256, 0, stream>>>(b.hist);
   CG_LAUNCH_CHECK(debug, stream);
@@ -225,7 +259,7 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
     sort_onesweep_pass<K><<<unsigned(ntiles), SORT_THREADS, sizeof(SortSmem<K>), stream>>>(
-        b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, 8 * p,
+        b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, bpp * p, dmask,
         b.hist + p * 256, b.ticket + p, b.status + size_t(p) * ntiles * 256);
     CG_LAUNCH_CHECK(debug, stream);
     cur ^= 1;
