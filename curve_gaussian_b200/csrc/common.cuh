@@ -78,6 +78,44 @@ struct __align__(16) Rec {
 };
 static_assert(sizeof(Rec) == 48, "record must stay 48 bytes");
 
+#ifdef __CUDACC__
+// Can this instance contribute to ANY pixel centre of the block [bx0,bx1] x [by0,by1]?
+//
+// A pixel contributes only if alpha = min(0.99, o*exp(power)) >= 1/255 (forward.cu:361-363), i.e.
+// q(d) = -power = 0.5 d^T Q d <= tau with tau = ln(255 o). q is convex with its minimum (0) at the
+// splat centre, so its minimum over the block is 0 if the centre is inside, and otherwise lies on the
+// block edge(s) facing the centre, where it is a clamped 1-D quadratic. The instance is skipped only if
+// that minimum exceeds tau by more than a bound on the fp32 evaluation error of `power` anywhere in
+// the block (E below) plus 2e-3; NaNs and non-positive-definite conics are never skipped. Skipping is
+// therefore invisible in the results (bit-identical images, n_contrib and gradients).
+__device__ __forceinline__ bool block_candidate(float cx, float cy, float A, float B, float C, float o,
+                                                float bx0, float bx1, float by0, float by1) {
+  const float chk = cx + cy + A + B + C + o;
+  if (chk != chk) return true;                           // NaN anywhere: let the exact path decide
+  if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true;
+  if (o <= 0.f) return false;                            // alpha <= 0 < 1/255 for every pixel
+  const float tau = fmaxf(__logf(255.0f * o), 0.0f) + 2e-3f;
+  const float dxn = fminf(fmaxf(cx, bx0), bx1) - cx;     // offset to the nearest block column (0 if inside)
+  const float dyn = fminf(fmaxf(cy, by0), by1) - cy;
+  const float Dx = fmaxf(fabsf(bx0 - cx), fabsf(bx1 - cx));
+  const float Dy = fmaxf(fabsf(by0 - cy), fabsf(by1 - cy));
+  const float E = 1e-6f * (A + C + 2.f * fabsf(B)) * (Dx * Dx + Dy * Dy);
+  float qmin = 0.f;
+  if (dxn != 0.f || dyn != 0.f) {
+    qmin = __int_as_float(0x7f800000);
+    if (dxn != 0.f) {
+      const float dy = fminf(fmaxf(__fdividef(-B * dxn, C), by0 - cy), by1 - cy);
+      qmin = 0.5f * (A * dxn * dxn + C * dy * dy) + B * dxn * dy;
+    }
+    if (dyn != 0.f) {
+      const float dx = fminf(fmaxf(__fdividef(-B * dyn, A), bx0 - cx), bx1 - cx);
+      qmin = fminf(qmin, 0.5f * (A * dx * dx + C * dyn * dyn) + B * dx * dyn);
+    }
+  }
+  return !(qmin > tau + E);
+}
+#endif
+
 struct GeomState {
   float2* xy;
   float4* conic_o;
@@ -126,13 +164,11 @@ struct ImgState {
 struct BinKeep {
   Rec* rec;
   uint32_t* point_list;
-  float4* cull;   // per instance {x, y, hx, hy}: conservative box of the pixels it can contribute to
   static BinKeep carve(void* base, int64_t R, size_t* bytes) {
     Carver c(base);
     BinKeep b;
     b.rec = c.take<Rec>(R + 1);
     b.point_list = c.take<uint32_t>(R + 1);
-    b.cull = c.take<float4>(R + 1);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }

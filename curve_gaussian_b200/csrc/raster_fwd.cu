@@ -247,20 +247,11 @@ rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_
   keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
 }
 
-// Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry + cull box.
-//
-// The cull box {x, y, hx, hy} bounds, conservatively, the pixels this instance can
-// contribute to. A pixel contributes only if alpha = min(0.99, o*exp(power)) >= 1/255
-// (forward.cu:361-363), i.e. power >= -tau with tau = ln(255*o); {d : 0.5 d^T Q d <= tau}
-// is an ellipse whose axis-aligned half extents are sqrt(2 tau Sxx), sqrt(2 tau Syy) with
-// S = Q^-1. The box is inflated (1e-4 relative + 0.05 px) far beyond the fp32 error of
-// `power`, and degenerate inputs (NaN, non-positive-definite conic) get an infinite box, so
-// skipping an instance whose box misses a warp's pixel block never changes a result bit.
+// Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry.
 __global__ void __launch_bounds__(256)
 gather_records(int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint32_t* __restrict__ sorted_vals,
                GeomState g, const float* __restrict__ colors, const float* __restrict__ all_map,
-               uint2* __restrict__ ranges, Rec* __restrict__ rec, uint32_t* __restrict__ point_list,
-               float4* __restrict__ cull) {
+               uint2* __restrict__ ranges, Rec* __restrict__ rec, uint32_t* __restrict__ point_list) {
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
   {
@@ -283,12 +274,6 @@ gather_records(int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint3
   out[0] = make_float4(xy.x, xy.y, co.x, co.y);
   out[1] = make_float4(co.z, co.w, __ldg(colors + id), 1.f / g.depth[id]);
   out[2] = mp;
-  const float det_q = co.x * co.z - co.y * co.y;
-  const float tau = fmaxf(logf(255.0f * co.w), 0.0f);   // NaN (o <= 0) -> 0: only d == 0 could ever pass
-  float hx = sqrtf(2.0f * tau * (co.z / det_q)) * 1.0001f + 0.05f;
-  float hy = sqrtf(2.0f * tau * (co.x / det_q)) * 1.0001f + 0.05f;
-  if (!(det_q > 0.0f) || !(hx >= 0.0f) || !(hy >= 0.0f)) hx = hy = __int_as_float(0x7f800000);
-  cull[i] = make_float4(xy.x, xy.y, hx, hy);
 }
 
 // ---------------------------------------------------------------------------
@@ -326,18 +311,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 constexpr int BATCH = 256;
 
 // One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block. The tile's
-// sorted records (and their cull boxes) are contiguous spans; thread 0 streams them into a
-// 2-deep shared ring with cp.async.bulk while all threads blend the previous batch.
-// Each warp first tests 32 cull boxes at a time (one per lane) against its pixel block and
-// only walks the instances whose box overlaps it, in list order (forward.cu:331-396 semantics).
+// sorted records are one contiguous span; thread 0 streams it into a 2-deep shared ring with
+// cp.async.bulk while all threads blend the previous batch. Each warp first tests 32 records
+// at a time (one per lane, block_candidate in common.cuh) against its pixel block and only
+// walks the instances that can reach it, in list order (forward.cu:331-396 semantics).
 template <bool GEO>
 __global__ void __launch_bounds__(256)
-blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, const float4* __restrict__ cull,
-          int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
+blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
           uint32_t* __restrict__ tile_maxc) {
   __shared__ __align__(128) Rec s_rec[2][BATCH];
-  __shared__ __align__(16) float4 s_cull[2][BATCH];
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ uint32_t s_maxc;
 
@@ -365,9 +348,8 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, const f
   __syncthreads();
   if (tid == 0 && rounds > 0) {
     const uint32_t nb = uint32_t(min(BATCH, total));
-    mbar_expect_tx(&s_full[0], nb * uint32_t(sizeof(Rec) + sizeof(float4)));
+    mbar_expect_tx(&s_full[0], nb * uint32_t(sizeof(Rec)));
     bulk_g2s(&s_rec[0][0], rec + range.x, nb * uint32_t(sizeof(Rec)), &s_full[0]);
-    bulk_g2s(&s_cull[0][0], cull + range.x, nb * uint32_t(sizeof(float4)), &s_full[0]);
   }
 
   bool done = !inside;
@@ -386,13 +368,11 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, const f
     if (tid == 0 && b + 1 < rounds) {
       const uint32_t nb = uint32_t(min(BATCH, todo - BATCH));
       const size_t off = size_t(range.x) + size_t(b + 1) * BATCH;
-      mbar_expect_tx(&s_full[(b + 1) & 1], nb * uint32_t(sizeof(Rec) + sizeof(float4)));
+      mbar_expect_tx(&s_full[(b + 1) & 1], nb * uint32_t(sizeof(Rec)));
       bulk_g2s(&s_rec[(b + 1) & 1][0], rec + off, nb * uint32_t(sizeof(Rec)), &s_full[(b + 1) & 1]);
-      bulk_g2s(&s_cull[(b + 1) & 1][0], cull + off, nb * uint32_t(sizeof(float4)), &s_full[(b + 1) & 1]);
     }
     mbar_wait(&s_full[b & 1], (b >> 1) & 1);
     const Rec* batch = s_rec[b & 1];
-    const float4* boxes = s_cull[b & 1];
     const int n = min(BATCH, todo);
     const uint32_t pos0 = uint32_t(b) * BATCH;
     for (int r = 0; r < n; r += 32) {
@@ -400,8 +380,9 @@ blend_fwd(const uint2* __restrict__ ranges, const Rec* __restrict__ rec, const f
       const int idx = r + int(lane);
       bool cand = false;
       if (idx < n) {
-        const float4 c = boxes[idx];
-        cand = !(c.x + c.z < bx0 || c.x - c.z > bx1 || c.y + c.w < by0 || c.y - c.w > by1);
+        const float4 ca = *reinterpret_cast<const float4*>(&batch[idx].x);
+        const float2 cb = *reinterpret_cast<const float2*>(&batch[idx].cc);
+        cand = block_candidate(ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, bx0, bx1, by0, by1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, cand);
       while (mask) {
@@ -533,16 +514,16 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     const unsigned rb = unsigned((R + 255) / 256);
     { StageTimer t_(ST_GATHER, st, 1);
     gather_records<<<rb, 256, 0, st>>>(R, bs.is.keys[cur], bs.is.vals[cur], g, colors,
-                                       s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list, bk.cull); }
+                                       s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   dim3 grid(gx, gy), block(TILE_PIX);
   StageTimer t_blend(ST_BLEND_FWD, st, 1);
   if (s->render_geo)
-    blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, bk.rec, bk.cull, W, H, s->bg, out_color, out_invd, out_map,
+    blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map,
                                             im.final_T, im.n_contrib, im.tile_maxc);
   else
-    blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, bk.rec, bk.cull, W, H, s->bg, out_color, out_invd, out_map,
+    blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, bk.rec, W, H, s->bg, out_color, out_invd, out_map,
                                              im.final_T, im.n_contrib, im.tile_maxc);
   CG_LAUNCH_CHECK(s->debug, st);
   return CG_OK;
