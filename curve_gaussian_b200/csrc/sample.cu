@@ -218,7 +218,7 @@ __device__ __forceinline__ Local local_state(const Curve& k, float t, float N1, 
   return L;
 }
 
-// Backward in ONE pass over the Gaussians plus a per-curve finalisation.
+// Backward = one pass over the Gaussians + one pass over the curves.
 //
 // The two whole-tensor norms couple every Gaussian through two scalars,
 //   K2 = sum g2.v2      K1 = sum g1.v1 + (sum (g2 x tau).v1 - K2 * sum (v2 x tau).v1) / N2,
@@ -227,133 +227,130 @@ __device__ __forceinline__ Local local_state(const Curve& k, float t, float N1, 
 //   U = v1 x gc_a + rot((g1 + gc_a x tau)/N1) + (v0 terms)     rot(a) = (-a.y, a.x, 0)
 //   V = v1 x gc_b + rot((gc_b x tau)/N1)
 //   W = rot(v1/N1)
-// so one kernel accumulates, per curve, the control-point sums of U, V and W (and the
-// position / scale terms, folded into U) together with the four global sums, and a tiny
-// second kernel combines them once K1, K2 are known. A CTA owns whole curves (256/n of
-// them) and reduces their samples through shared memory in a fixed order: no atomics on
-// the outputs, bit-reproducible gradients.
-constexpr int SB_THREADS = 256;
-constexpr int SB_VALS = 37;   // 12 (U) + 12 (V) + 12 (W) + dL/dwidth
+// sample_bwd_point (thread per Gaussian, the heavy quaternion adjoint) writes gpos, gfront, U,
+// V, W to a structure-of-arrays scratch and block-reduces the four global sums;
+// sample_bwd_curve (warp per curve) then folds them into the control points with the
+// Bernstein / tangent weights, in a fixed order: no atomics on the outputs, bit-reproducible
+// gradients, and the heavy math runs once instead of twice (reduce pass + main pass).
+constexpr int SB_PT = 14;   // gpos 3, gfront 3, U 3, V 3, W 2 (W.z == 0)
 
-__global__ void __launch_bounds__(SB_THREADS, 2)
-sample_bwd_partial(int64_t B, int n, int cpb, const float* __restrict__ cp, const uint8_t* __restrict__ is_bezier,
-                   const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
-                   const float* __restrict__ dL_dxyz, const float* __restrict__ dL_drot,
-                   const float* __restrict__ dL_dscaling, float* __restrict__ part, double* __restrict__ sums) {
-  __shared__ float s_v[SB_VALS][SB_THREADS + 1];
+__global__ void __launch_bounds__(256)
+sample_bwd_point(int64_t B, int n, const float* __restrict__ cp, const uint8_t* __restrict__ is_bezier,
+                 const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
+                 const float* __restrict__ dL_dxyz, const float* __restrict__ dL_drot,
+                 const float* __restrict__ dL_dscaling, float* __restrict__ pt, double* __restrict__ sums) {
   __shared__ double s_red[8];
-  const int tid = threadIdx.x;
-  const int per = n < SB_THREADS ? n : SB_THREADS;   // threads that serve one curve
-  const int lc = tid / per;                          // local curve of this thread
-  const int64_t b = int64_t(blockIdx.x) * cpb + lc;
-  const bool active = lc < cpb && b < B;
+  const int64_t P = B * n;
+  const int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const float N1 = norms[0], N2 = norms[1];
-  // each thread accumulates into its own shared-memory column (one Gaussian per thread unless n > 256)
-#pragma unroll
-  for (int i = 0; i < SB_VALS; ++i) s_v[i][tid] = 0.f;
   double s[4] = {0.0, 0.0, 0.0, 0.0};
-  if (active) {
+  if (g < P) {
+    const int64_t b = g / n;
+    const int m = int(g - b * n);
     const Curve k = load_curve(cp, is_bezier, b);
-    for (int m = tid - lc * per; m < n; m += per) {
-      const int64_t g = b * n + m;
-      const float t = tt[m];
-      V3 gpos = v3(0, 0, 0), gfront = v3(0, 0, 0);
-      V3 U = v3(0, 0, 0), V = v3(0, 0, 0), Wv = v3(0, 0, 0);
-      if (dL_dxyz) gpos = v3(dL_dxyz[3 * g], dL_dxyz[3 * g + 1], dL_dxyz[3 * g + 2]);
-      if (dL_dscaling) {
-        const V3 pos = curve_point(k, t), front = curve_point(k, t - half_step);
-        const V3 d = pos - front;
-        const float dist = sqrtf(dot(d, d));
-        if (dist > 0.f) {
-          const V3 gd = (dL_dscaling[3 * g] / dist) * d;
-          gpos = gpos + gd;
-          gfront = v3(-gd.x, -gd.y, -gd.z);
-        }
-        s_v[36][tid] += dL_dscaling[3 * g + 1] + dL_dscaling[3 * g + 2];
-      }
-      if (dL_drot) {
-        const float4 gq4 = reinterpret_cast<const float4*>(dL_drot)[g];
-        const float gq[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
-        const Local L = local_state(k, t, N1, N2, gq);
-        const V3 g0 = v3(L.gm[0][0], L.gm[1][0], L.gm[2][0]);
-        const V3 g1 = v3(L.gm[0][1], L.gm[1][1], L.gm[2][1]);
-        const V3 g2 = v3(L.gm[0][2], L.gm[1][2], L.gm[2][2]);
-        const V3 tau = L.f.tau;
-        s[0] += double(dot(g2, L.v2));
-        s[1] += double(dot(g1, L.v1));
-        s[2] += double(dot(cross(g2, tau), L.v1));
-        s[3] += double(dot(cross(L.v2, tau), L.v1));
-        const float iN1 = 1.f / N1, iN2 = 1.f / N2;
-        const V3 gc_a = iN2 * g2, gc_b = iN2 * L.v2;
-        const V3 ga_a = iN1 * (g1 + cross(gc_a, tau));
-        const V3 ga_b = iN1 * cross(gc_b, tau);
-        const V3 ga_c = iN1 * L.v1;
-        U = cross(L.v1, gc_a);
-        U.x -= ga_a.y; U.y += ga_a.x;
-        V = cross(L.v1, gc_b);
-        V.x -= ga_b.y; V.y += ga_b.x;
-        Wv = v3(-ga_c.y, ga_c.x, 0.f);
-        // v0 = tau / (|tau| + eps)
-        const float len = L.f.len, inv = 1.f / (len + 1e-8f);
-        U = U + inv * g0;
-        if (len > 0.f) U = U - (dot(g0, tau) * inv * inv / len) * tau;
-      }
-      // chain into the control points
-      float w[4], wf[4];
-      point_weights(k.bez, t, w);
-      point_weights(k.bez, t - half_step, wf);
-      float cw[4];   // d tau / d P_j
-      if (k.bez) {
-        float tw[3];
-        tangent_weights(t, tw);
-        cw[0] = -tw[0]; cw[1] = tw[0] - tw[1]; cw[2] = tw[1] - tw[2]; cw[3] = tw[2];
-      } else { cw[0] = -1.f; cw[1] = 0.f; cw[2] = 0.f; cw[3] = 1.f; }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const V3 u = w[j] * gpos + wf[j] * gfront + cw[j] * U;
-        s_v[3 * j][tid] += u.x; s_v[3 * j + 1][tid] += u.y; s_v[3 * j + 2][tid] += u.z;
-        s_v[12 + 3 * j][tid] += cw[j] * V.x; s_v[12 + 3 * j + 1][tid] += cw[j] * V.y; s_v[12 + 3 * j + 2][tid] += cw[j] * V.z;
-        s_v[24 + 3 * j][tid] += cw[j] * Wv.x; s_v[24 + 3 * j + 1][tid] += cw[j] * Wv.y; s_v[24 + 3 * j + 2][tid] += cw[j] * Wv.z;
+    const float t = tt[m];
+    V3 gpos = v3(0, 0, 0), gfront = v3(0, 0, 0);
+    V3 U = v3(0, 0, 0), V = v3(0, 0, 0), Wv = v3(0, 0, 0);
+    if (dL_dxyz) gpos = v3(dL_dxyz[3 * g], dL_dxyz[3 * g + 1], dL_dxyz[3 * g + 2]);
+    if (dL_dscaling) {
+      const V3 pos = curve_point(k, t), front = curve_point(k, t - half_step);
+      const V3 d = pos - front;
+      const float dist = sqrtf(dot(d, d));
+      if (dist > 0.f) {
+        const V3 gd = (dL_dscaling[3 * g] / dist) * d;
+        gpos = gpos + gd;
+        gfront = v3(-gd.x, -gd.y, -gd.z);
       }
     }
-  }
-  __syncthreads();
-  // (curve, value) tasks are spread over groups of 8 lanes: fixed summation order, no atomics
-  const int lane8 = tid & 7;
-  const int ntasks = cpb * SB_VALS;
-  for (int task = tid >> 3; task < ntasks; task += SB_THREADS / 8) {
-    const int c = task / SB_VALS, i = task - c * SB_VALS;
-    const int64_t bc = int64_t(blockIdx.x) * cpb + c;
-    float v = 0.f;
-    for (int j = lane8; j < per; j += 8) v += s_v[i][c * per + j];
-    // groups of one warp may run different trip counts: synchronise the 8 lanes of this group only
-    const uint32_t gmask = 0xffu << (tid & 24);
-    v += __shfl_xor_sync(gmask, v, 4);
-    v += __shfl_xor_sync(gmask, v, 2);
-    v += __shfl_xor_sync(gmask, v, 1);
-    if (lane8 == 0 && bc < B) part[bc * SB_VALS + i] = v;
+    if (dL_drot) {
+      const float4 gq4 = reinterpret_cast<const float4*>(dL_drot)[g];
+      const float gq[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
+      const Local L = local_state(k, t, N1, N2, gq);
+      const V3 g0 = v3(L.gm[0][0], L.gm[1][0], L.gm[2][0]);
+      const V3 g1 = v3(L.gm[0][1], L.gm[1][1], L.gm[2][1]);
+      const V3 g2 = v3(L.gm[0][2], L.gm[1][2], L.gm[2][2]);
+      const V3 tau = L.f.tau;
+      s[0] = double(dot(g2, L.v2));
+      s[1] = double(dot(g1, L.v1));
+      s[2] = double(dot(cross(g2, tau), L.v1));
+      s[3] = double(dot(cross(L.v2, tau), L.v1));
+      const float iN1 = 1.f / N1, iN2 = 1.f / N2;
+      const V3 gc_a = iN2 * g2, gc_b = iN2 * L.v2;
+      const V3 ga_a = iN1 * (g1 + cross(gc_a, tau));
+      const V3 ga_b = iN1 * cross(gc_b, tau);
+      const V3 ga_c = iN1 * L.v1;
+      U = cross(L.v1, gc_a);
+      U.x -= ga_a.y; U.y += ga_a.x;
+      V = cross(L.v1, gc_b);
+      V.x -= ga_b.y; V.y += ga_b.x;
+      Wv = v3(-ga_c.y, ga_c.x, 0.f);
+      // v0 = tau / (|tau| + eps)
+      const float len = L.f.len, inv = 1.f / (len + 1e-8f);
+      U = U + inv * g0;
+      if (len > 0.f) U = U - (dot(g0, tau) * inv * inv / len) * tau;
+    }
+    const float o[SB_PT] = {gpos.x, gpos.y, gpos.z, gfront.x, gfront.y, gfront.z, U.x, U.y, U.z, V.x, V.y, V.z, Wv.x, Wv.y};
+#pragma unroll
+    for (int i = 0; i < SB_PT; ++i) pt[int64_t(i) * P + g] = o[i];
   }
   if (dL_drot) {
     for (int i = 0; i < 4; ++i) {
       const double t = block_sum(s[i], s_red);
-      if (tid == 0) atomicAdd(&sums[i], t);
+      if (threadIdx.x == 0) atomicAdd(&sums[i], t);
     }
   }
 }
 
+// One warp per curve; lanes stride over the curve's samples (coalesced reads of the scratch).
 __global__ void __launch_bounds__(256)
-sample_bwd_finish(int64_t B, const float* __restrict__ width, const float* __restrict__ norms,
-                  const double* __restrict__ sums, const float* __restrict__ part, float* __restrict__ dL_dcp,
-                  float* __restrict__ dL_dwidth) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= B * 13) return;
-  const int64_t b = i / 13;
-  const int c = int(i - b * 13);
-  const float* p = part + b * SB_VALS;
-  if (c == 12) { dL_dwidth[b] = p[36] * expf(width[b]); return; }
+sample_bwd_curve(int64_t B, int n, const float* __restrict__ width, const uint8_t* __restrict__ is_bezier,
+                 const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
+                 const double* __restrict__ sums, const float* __restrict__ pt, const float* __restrict__ dL_dscaling,
+                 float* __restrict__ dL_dcp, float* __restrict__ dL_dwidth) {
+  const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int64_t P = B * n;
+  const bool bez = is_bezier ? (is_bezier[b] != 0) : true;
   const float K2 = float(sums[0]);
   const float K1 = float(sums[1] + (sums[2] - sums[0] * sums[3]) / double(norms[1]));
-  dL_dcp[b * 12 + c] = p[c] - K2 * p[12 + c] - K1 * p[24 + c];
+  float acc[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) acc[i] = 0.f;
+  for (int m = lane; m < n; m += 32) {
+    const int64_t g = b * n + m;
+    const float t = tt[m];
+    float v[SB_PT];
+#pragma unroll
+    for (int i = 0; i < SB_PT; ++i) v[i] = __ldg(pt + int64_t(i) * P + g);
+    // gtau = U - K2 V - K1 W
+    const float gtx = v[6] - K2 * v[9] - K1 * v[12];
+    const float gty = v[7] - K2 * v[10] - K1 * v[13];
+    const float gtz = v[8] - K2 * v[11];
+    float w[4], wf[4], cw[4];
+    point_weights(bez, t, w);
+    point_weights(bez, t - half_step, wf);
+    if (bez) {
+      float tw[3];
+      tangent_weights(t, tw);
+      cw[0] = -tw[0]; cw[1] = tw[0] - tw[1]; cw[2] = tw[1] - tw[2]; cw[3] = tw[2];
+    } else { cw[0] = -1.f; cw[1] = 0.f; cw[2] = 0.f; cw[3] = 1.f; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[3 * j] += w[j] * v[0] + wf[j] * v[3] + cw[j] * gtx;
+      acc[3 * j + 1] += w[j] * v[1] + wf[j] * v[4] + cw[j] * gty;
+      acc[3 * j + 2] += w[j] * v[2] + wf[j] * v[5] + cw[j] * gtz;
+    }
+    if (dL_dscaling) acc[12] += dL_dscaling[3 * g + 1] + dL_dscaling[3 * g + 2];
+  }
+#pragma unroll
+  for (int i = 0; i < 13; ++i)
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) dL_dcp[b * 12 + i] = acc[i];
+    dL_dwidth[b] = acc[12] * expf(width[b]);
+  }
 }
 
 }  // namespace cg
@@ -362,9 +359,9 @@ using namespace cg;
 
 extern "C" {
 
-size_t cg_sample_scratch_bytes(int64_t B, int32_t) {
-  // 8 doubles of global sums + the per-curve partial sums of the backward
-  return 128 + size_t(B < 1 ? 1 : B) * SB_VALS * sizeof(float);
+size_t cg_sample_scratch_bytes(int64_t B, int32_t n) {
+  // 8 doubles of global sums + the per-Gaussian structure-of-arrays scratch of the backward
+  return 128 + size_t(B < 1 ? 1 : B) * size_t(n < 1 ? 1 : n) * SB_PT * sizeof(float);
 }
 
 int cg_sample_fwd(int64_t B, int32_t n, const float* curve_points, const float* width, const uint8_t* is_bezier,
@@ -401,15 +398,13 @@ int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* 
   double* sums = reinterpret_cast<double*>(scratch);
   const int64_t P = B * n;
   CG_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(double), st));
-  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 128);
-  const int cpb = n < SB_THREADS ? SB_THREADS / n : 1;
+  float* pt = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 128);
   StageTimer t_(ST_SAMPLE_BWD, st, 2);
-  sample_bwd_partial<<<unsigned((B + cpb - 1) / cpb), SB_THREADS, 0, st>>>(B, n, cpb, curve_points, is_bezier, t, half_step,
-                                                                         norms, dL_dxyz, dL_drotation, dL_dscaling, part,
-                                                                         sums);
+  sample_bwd_point<<<unsigned((P + 255) / 256), 256, 0, st>>>(B, n, curve_points, is_bezier, t, half_step, norms, dL_dxyz,
+                                                             dL_drotation, dL_dscaling, pt, sums);
   CG_LAUNCH_CHECK(0, st);
-  sample_bwd_finish<<<unsigned((B * 13 + 255) / 256), 256, 0, st>>>(B, width, norms, sums, part, dL_dcurve_points,
-                                                                   dL_dwidth);
+  sample_bwd_curve<<<unsigned((B * 32 + 255) / 256), 256, 0, st>>>(B, n, width, is_bezier, t, half_step, norms, sums, pt,
+                                                                  dL_dscaling, dL_dcurve_points, dL_dwidth);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }

@@ -17,6 +17,14 @@ namespace cg {
 
 namespace {
 
+// Optional per-phase clock instrumentation (scripts/sort_phases.cu defines CG_SORT_TIMING); compiled out otherwise.
+#ifdef CG_SORT_TIMING
+__device__ long long* g_sort_ticks = nullptr;   // [tile][8]
+#define CG_SORT_TICK(n) do { if (threadIdx.x == 0 && g_sort_ticks) g_sort_ticks[size_t(s.tile_id) * 8 + (n)] = clock64(); } while (0)
+#else
+#define CG_SORT_TICK(n) do { } while (0)
+#endif
+
 constexpr uint32_t FLAG_SHIFT = 30;
 constexpr uint32_t VALUE_MASK = (1u << FLAG_SHIFT) - 1u;
 constexpr uint32_t FLAG_AGG = 1u;   // tile-local count published
@@ -84,6 +92,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
   for (int i = tid; i < WARPS * 257; i += SORT_THREADS) (&s.whist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s.tile_id;
+  CG_SORT_TICK(0);
   const int64_t tile_base = int64_t(tile) * SORT_TILE;
   const int64_t warp_base = tile_base + int64_t(warp) * (32 * SORT_ITEMS);
 
@@ -98,6 +107,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     v[i] = ok ? vals_in[idx] : 0u;
   }
 
+  CG_SORT_TICK(1);   // (the loads are only waited for at first use, inside the ranking)
   // Stable in-warp ranking (items are in memory order). For each item the lanes holding the
   // same digit form a peer group (match.any); the group's first lane bumps the warp's digit
   // counter with ONE shared-memory atomic that returns the group's base. The atomics of
@@ -124,6 +134,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     }
   }
   __syncthreads();
+  CG_SORT_TICK(2);
 
   // Thread d owns digit d: exclusive scan across warps, tile count, look-back.
   {
@@ -158,12 +169,16 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     const uint32_t lstart = wb + inc - total;
     s.local_start[d] = lstart;
 
+    CG_SORT_TICK(3);
     // Decoupled look-back, LB predecessors per round trip: all tiles of the first wave publish
     // their aggregates at about the same time, so a one-at-a-time walk ripples through
     // ~ntiles/2 dependent L2 round trips; independent loads of a window cut that by LB.
     uint32_t excl = 0;
     if (tile > 0 && live) {
-      constexpr int LB = 16;
+#ifndef CG_SORT_LB
+#define CG_SORT_LB 4
+#endif
+      constexpr int LB = CG_SORT_LB;
       int64_t t = int64_t(tile) - 1;
       bool done = false;
       while (!done) {
@@ -187,12 +202,16 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
           }
         }
         t -= used;
+#ifdef CG_SORT_BACKOFF
+        if (!done && used == 0) __nanosleep(CG_SORT_BACKOFF);
+#endif
       }
       atomicExch(st, (FLAG_INC << FLAG_SHIFT) | ((excl + total) & VALUE_MASK));
     }
     s.gbase[d] = int32_t(digit_base[d] + excl) - int32_t(lstart);
   }
   __syncthreads();
+  CG_SORT_TICK(4);
 
   // Scatter into shared memory at the tile-local sorted position.
 #pragma unroll
@@ -206,6 +225,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     }
   }
   __syncthreads();
+  CG_SORT_TICK(5);
 
   // Coalesced write-out: consecutive threads write consecutive slots of a digit run.
   int64_t rem = R - tile_base;
@@ -217,6 +237,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     keys_out[g] = key;
     vals_out[g] = s.vals[j];
   }
+  CG_SORT_TICK(6);
 }
 
 }  // namespace

@@ -52,7 +52,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_red) {
 //   [0] sum ssim  [1] sum sq over gt>thr  [2] sum sq over gt<=thr  [3] count gt>thr
 //   [4] CTA ticket (low 32 bits)  [5] loss  [6] w_pos  [7] w_neg
 template <bool LOSS>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 ssim_fwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, const float* __restrict__ img2,
                 float* __restrict__ ssim_map, float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
                 float* __restrict__ dm_dsigma12, double* __restrict__ stats, float* __restrict__ loss_out) {
@@ -96,24 +96,25 @@ ssim_fwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, co
   // vertical pass: RUN consecutive output rows per thread
   const int lx = threadIdx.x & 31;
   const int ly0 = (threadIdx.x >> 5) * RUN;
-  float col[5][WIN];
+  // one channel at a time: a 14-value column window and 4 accumulators are live, not 5 x 14
+  float acc[5][RUN];
 #pragma unroll
-  for (int c = 0; c < 5; ++c)
+  for (int c = 0; c < 5; ++c) {
+    float col[WIN];
 #pragma unroll
-    for (int k = 0; k < WIN; ++k) col[c][k] = hq[c][ly0 + k][lx];
+    for (int k = 0; k < WIN; ++k) col[k] = hq[c][ly0 + k][lx];
+#pragma unroll
+    for (int r = 0; r < RUN; ++r) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 11; ++k) v += c_tap[k] * col[r + k];
+      acc[c][r] = v;
+    }
+  }
   double a_ssim = 0.0, a_pos = 0.0, a_neg = 0.0, a_cnt = 0.0;
 #pragma unroll
   for (int r = 0; r < RUN; ++r) {
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_tap[k];
-      mu1 += g * col[0][r + k];
-      mu2 += g * col[1][r + k];
-      e11 += g * col[2][r + k];
-      e22 += g * col[3][r + k];
-      e12 += g * col[4][r + k];
-    }
+    const float mu1 = acc[0][r], mu2 = acc[1][r], e11 = acc[2][r], e22 = acc[3][r], e12 = acc[4][r];
     const int ly = ly0 + r;
     const int x = x0 + lx, y = y0 + ly;
     if (x < W && y < H) {

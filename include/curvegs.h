@@ -154,6 +154,8 @@ int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
  *   xyz (P,3), rotation (P,4) un-normalised w>=0 quaternion, scaling (P,3).
  * norms (2 floats, device) receives the two whole-tensor Frobenius norms
  * (:190,:192) and must be kept for the backward. */
+/* scratch: cg_sample_scratch_bytes(B, n) for the backward (global sums + a per-Gaussian
+ * structure-of-arrays work area); the forward only uses its first 64 bytes. 8-byte aligned. */
 size_t cg_sample_scratch_bytes(int64_t B, int32_t n);
 int cg_sample_fwd(int64_t B, int32_t n, const float* curve_points, const float* width,
                   const uint8_t* is_bezier, const float* t, float half_step,
