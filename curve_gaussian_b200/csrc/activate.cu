@@ -43,75 +43,90 @@ activate_fwd(int64_t P, int n, const float* __restrict__ xyz, const float* __res
                   c0 * vm[2] + c1 * vm[6] + c2 * vm[10], 1.0f);
 }
 
-// One warp per curve (lanes stride over its samples) so the per-curve opacity gradient is a
-// shuffle reduction, not an atomic scatter.
+// Backward: one thread per Gaussian for everything per-Gaussian (coalesced, fully parallel), then one
+// warp per curve for the only per-curve quantity, the opacity-logit gradient, as a fixed-order shuffle
+// reduction (no atomic scatter, reproducible).
 __global__ void __launch_bounds__(256)
-activate_bwd(int64_t B, int n, const float* __restrict__ xyz, const float* __restrict__ rot,
-             const float* __restrict__ scaling, const float* __restrict__ opacity_logit,
-             const float* __restrict__ mask_logit, float mask_thr, const float* __restrict__ campos,
-             const float* __restrict__ vm, const float* __restrict__ g_rot_n, const float* __restrict__ g_opacity,
-             const float* __restrict__ g_scales, const float* __restrict__ g_all_map,
-             float* __restrict__ g_rot, float* __restrict__ g_scaling, float* __restrict__ g_opacity_logit,
-             float* __restrict__ g_mask_logit) {
+activate_bwd_point(int64_t P, int n, const float* __restrict__ xyz, const float* __restrict__ rot,
+                   const float* __restrict__ scaling, const float* __restrict__ opacity_logit,
+                   const float* __restrict__ mask_logit, float mask_thr, const float* __restrict__ campos,
+                   const float* __restrict__ vm, const float* __restrict__ g_rot_n, const float* __restrict__ g_opacity,
+                   const float* __restrict__ g_scales, const float* __restrict__ g_all_map,
+                   float* __restrict__ g_rot, float* __restrict__ g_scaling, float* __restrict__ g_mask_logit) {
+  const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (g >= P) return;
+  // ---- mask / opacity / scales
+  float m = 1.f, sm = 0.f;
+  if (mask_logit) {
+    sm = sigmoidf_(mask_logit[g]);
+    m = __fadd_rn(__fsub_rn(sm > mask_thr ? 1.f : 0.f, sm), sm);
+  }
+  float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f;
+  if (g_scales) { gs0 = g_scales[3 * g]; gs1 = g_scales[3 * g + 1]; gs2 = g_scales[3 * g + 2]; }
+  g_scaling[3 * g] = gs0 * m; g_scaling[3 * g + 1] = gs1 * m; g_scaling[3 * g + 2] = gs2 * m;
+  if (mask_logit && g_mask_logit) {
+    const float go = g_opacity ? g_opacity[g] : 0.f;
+    const float op = sigmoidf_(opacity_logit[g / n]);
+    const float gm = go * op + gs0 * scaling[3 * g] + gs1 * scaling[3 * g + 1] + gs2 * scaling[3 * g + 2];
+    g_mask_logit[g] = gm * sm * (1.f - sm);
+  }
+  // ---- rotation
+  const float4 q = reinterpret_cast<const float4*>(rot)[g];
+  const float nraw = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  const float nrm = fmaxf(nraw, 1e-12f);
+  const float r = q.x / nrm, i = q.y / nrm, j = q.z / nrm, k = q.w / nrm;
+  float4 gq = g_rot_n ? reinterpret_cast<const float4*>(g_rot_n)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g_all_map) {
+    const float4 ga = reinterpret_cast<const float4*>(g_all_map)[g];
+    // local = dir @ V[:3,:3]  ->  g_dir_r = sum_c ga_c * V[r][c]
+    float d0 = ga.x * vm[0] + ga.y * vm[1] + ga.z * vm[2];
+    float d1 = ga.x * vm[4] + ga.y * vm[5] + ga.z * vm[6];
+    float d2 = ga.x * vm[8] + ga.y * vm[9] + ga.z * vm[10];
+    const float S = r * r + i * i + j * j + k * k;
+    const float two_s = 2.0f / S;
+    const float c0 = 1.f - two_s * (j * j + k * k), c1 = two_s * (i * j + k * r), c2 = two_s * (i * k - j * r);
+    const float tx = campos[0] - xyz[3 * g], ty = campos[1] - xyz[3 * g + 1], tz = campos[2] - xyz[3 * g + 2];
+    if (c0 * tx + c1 * ty + c2 * tz < 0.0f) { d0 = -d0; d1 = -d1; d2 = -d2; }
+    // c0 = 1 - ts*(jj+kk), c1 = ts*(ij+kr), c2 = ts*(ik-jr), ts = 2/S
+    const float e0 = j * j + k * k, e1 = i * j + k * r, e2 = i * k - j * r;
+    const float g_ts = -d0 * e0 + d1 * e1 + d2 * e2;
+    const float g_S = -g_ts * two_s / S;
+    gq.x += two_s * (d1 * k - d2 * j) + 2.f * r * g_S;
+    gq.y += two_s * (d1 * j + d2 * k) + 2.f * i * g_S;
+    gq.z += two_s * (-2.f * j * d0 + d1 * i - d2 * r) + 2.f * j * g_S;
+    gq.w += two_s * (-2.f * k * d0 + d1 * r + d2 * i) + 2.f * k * g_S;
+  }
+  // through x / max(|x|, eps)
+  float4 out;
+  if (nraw > 1e-12f) {
+    const float dt = gq.x * r + gq.y * i + gq.z * j + gq.w * k;
+    out = make_float4((gq.x - r * dt) / nrm, (gq.y - i * dt) / nrm, (gq.z - j * dt) / nrm, (gq.w - k * dt) / nrm);
+  } else {
+    out = make_float4(gq.x / nrm, gq.y / nrm, gq.z / nrm, gq.w / nrm);
+  }
+  reinterpret_cast<float4*>(g_rot)[g] = out;
+}
+
+__global__ void __launch_bounds__(256)
+activate_bwd_curve(int64_t B, int n, const float* __restrict__ opacity_logit, const float* __restrict__ mask_logit,
+                   float mask_thr, const float* __restrict__ g_opacity, float* __restrict__ g_opacity_logit) {
   const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
-  const float op = sigmoidf_(opacity_logit[b]);
   float g_op_sum = 0.f;
-  for (int mi = lane; mi < n; mi += 32) {
-    const int64_t g = b * n + mi;
-    // ---- mask / opacity / scales
-    float m = 1.f, sm = 0.f;
-    if (mask_logit) {
-      sm = sigmoidf_(mask_logit[g]);
-      m = __fadd_rn(__fsub_rn(sm > mask_thr ? 1.f : 0.f, sm), sm);
+  if (g_opacity) {
+    for (int mi = lane; mi < n; mi += 32) {
+      const int64_t g = b * n + mi;
+      float m = 1.f;
+      if (mask_logit) {
+        const float sm = sigmoidf_(mask_logit[g]);
+        m = __fadd_rn(__fsub_rn(sm > mask_thr ? 1.f : 0.f, sm), sm);
+      }
+      g_op_sum += g_opacity[g] * m;
     }
-    const float go = g_opacity ? g_opacity[g] : 0.f;
-    float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f;
-    if (g_scales) { gs0 = g_scales[3 * g]; gs1 = g_scales[3 * g + 1]; gs2 = g_scales[3 * g + 2]; }
-    g_op_sum += go * m;
-    g_scaling[3 * g] = gs0 * m; g_scaling[3 * g + 1] = gs1 * m; g_scaling[3 * g + 2] = gs2 * m;
-    if (mask_logit && g_mask_logit) {
-      const float gm = go * op + gs0 * scaling[3 * g] + gs1 * scaling[3 * g + 1] + gs2 * scaling[3 * g + 2];
-      g_mask_logit[g] = gm * sm * (1.f - sm);
-    }
-    // ---- rotation
-    const float4 q = reinterpret_cast<const float4*>(rot)[g];
-    const float nraw = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
-    const float nrm = fmaxf(nraw, 1e-12f);
-    const float r = q.x / nrm, i = q.y / nrm, j = q.z / nrm, k = q.w / nrm;
-    float4 gq = g_rot_n ? reinterpret_cast<const float4*>(g_rot_n)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g_all_map) {
-      const float4 ga = reinterpret_cast<const float4*>(g_all_map)[g];
-      // local = dir @ V[:3,:3]  ->  g_dir_r = sum_c ga_c * V[r][c]
-      float d0 = ga.x * vm[0] + ga.y * vm[1] + ga.z * vm[2];
-      float d1 = ga.x * vm[4] + ga.y * vm[5] + ga.z * vm[6];
-      float d2 = ga.x * vm[8] + ga.y * vm[9] + ga.z * vm[10];
-      const float S = r * r + i * i + j * j + k * k;
-      const float two_s = 2.0f / S;
-      const float c0 = 1.f - two_s * (j * j + k * k), c1 = two_s * (i * j + k * r), c2 = two_s * (i * k - j * r);
-      const float tx = campos[0] - xyz[3 * g], ty = campos[1] - xyz[3 * g + 1], tz = campos[2] - xyz[3 * g + 2];
-      if (c0 * tx + c1 * ty + c2 * tz < 0.0f) { d0 = -d0; d1 = -d1; d2 = -d2; }
-      // c0 = 1 - ts*(jj+kk), c1 = ts*(ij+kr), c2 = ts*(ik-jr), ts = 2/S
-      const float e0 = j * j + k * k, e1 = i * j + k * r, e2 = i * k - j * r;
-      const float g_ts = -d0 * e0 + d1 * e1 + d2 * e2;
-      const float g_S = -g_ts * two_s / S;
-      gq.x += two_s * (d1 * k - d2 * j) + 2.f * r * g_S;
-      gq.y += two_s * (d1 * j + d2 * k) + 2.f * i * g_S;
-      gq.z += two_s * (-2.f * j * d0 + d1 * i - d2 * r) + 2.f * j * g_S;
-      gq.w += two_s * (-2.f * k * d0 + d1 * r + d2 * i) + 2.f * k * g_S;
-    }
-    // through x / max(|x|, eps)
-    float4 out;
-    if (nraw > 1e-12f) {
-      const float dt = gq.x * r + gq.y * i + gq.z * j + gq.w * k;
-      out = make_float4((gq.x - r * dt) / nrm, (gq.y - i * dt) / nrm, (gq.z - j * dt) / nrm, (gq.w - k * dt) / nrm);
-    } else {
-      out = make_float4(gq.x / nrm, gq.y / nrm, gq.z / nrm, gq.w / nrm);
-    }
-    reinterpret_cast<float4*>(g_rot)[g] = out;
   }
   for (int o = 16; o > 0; o >>= 1) g_op_sum += __shfl_xor_sync(0xffffffffu, g_op_sum, o);
+  const float op = sigmoidf_(opacity_logit[b]);
   if (lane == 0) g_opacity_logit[b] = g_op_sum * op * (1.f - op);
 }
 
@@ -151,11 +166,14 @@ int cg_activate_bwd(int64_t B, int32_t n, const float* xyz, const float* rotatio
   CG_ARG(xyz && rotation && scaling && opacity_logit && campos && viewmatrix && g_rotation && g_scaling &&
              g_opacity_logit, "activate_bwd pointers");
   CG_ARG(!mask_logit || g_mask_logit, "g_mask_logit required with mask_logit");
-  StageTimer t_(ST_ACTIVATE_BWD, st, 1);
-  activate_bwd<<<unsigned((B * 32 + 255) / 256), 256, 0, st>>>(B, n, xyz, rotation, scaling, opacity_logit, mask_logit,
-                                                              mask_thr, campos, viewmatrix, g_rot_n, g_opacity,
-                                                              g_scales, g_all_map, g_rotation, g_scaling,
-                                                              g_opacity_logit, g_mask_logit);
+  const int64_t P = B * n;
+  StageTimer t_(ST_ACTIVATE_BWD, st, 2);
+  activate_bwd_point<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, n, xyz, rotation, scaling, opacity_logit, mask_logit,
+                                                               mask_thr, campos, viewmatrix, g_rot_n, g_opacity, g_scales,
+                                                               g_all_map, g_rotation, g_scaling, g_mask_logit);
+  CG_LAUNCH_CHECK(0, st);
+  activate_bwd_curve<<<unsigned((B * 32 + 255) / 256), 256, 0, st>>>(B, n, opacity_logit, mask_logit, mask_thr,
+                                                                    g_opacity, g_opacity_logit);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }
