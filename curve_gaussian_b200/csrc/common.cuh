@@ -116,6 +116,36 @@ __device__ __forceinline__ bool block_candidate(float cx, float cy, float A, flo
 }
 #endif
 
+// Radix sort geometry (see sort.cu).
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
+constexpr int SORT_MAX_PASSES = 8;
+
+// Ping-pong buffers + look-back state of one radix sort of n (key, value) pairs.
+template <typename K>
+struct SortBufs {
+  K* keys[2];
+  uint32_t* vals[2];
+  uint32_t* hist;     // [SORT_MAX_PASSES][256] global digit histograms -> exclusive bases
+  uint32_t* ticket;   // [SORT_MAX_PASSES] dynamic tile id counters
+  uint32_t* status;   // [passes][ntiles][256] decoupled look-back words
+  size_t status_words;
+  static SortBufs carve(Carver& c, int64_t n) {
+    SortBufs b;
+    int64_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+    b.keys[0] = c.take<K>(n + 1);
+    b.keys[1] = c.take<K>(n + 1);
+    b.vals[0] = c.take<uint32_t>(n + 1);
+    b.vals[1] = c.take<uint32_t>(n + 1);
+    b.hist = c.take<uint32_t>(SORT_MAX_PASSES * 256);
+    b.ticket = c.take<uint32_t>(32);
+    b.status_words = size_t(sizeof(K)) * size_t(ntiles > 0 ? ntiles : 1) * 256;   // sizeof(K) = max passes
+    b.status = c.take<uint32_t>(b.status_words);
+    return b;
+  }
+};
+
 struct GeomState {
   float2* xy;
   float4* conic_o;
@@ -125,6 +155,7 @@ struct GeomState {
   uint32_t* blk_sum;
   uint32_t* blk_prefix;
   uint32_t* total;   // [0] = R
+  SortBufs<uint32_t> gs;   // the P Gaussians sorted by depth bits (value = Gaussian index), see BinScratch
   static GeomState carve(void* base, int64_t P, size_t* bytes) {
     Carver c(base);
     GeomState g;
@@ -137,6 +168,7 @@ struct GeomState {
     g.blk_sum = c.take<uint32_t>(nblk);
     g.blk_prefix = c.take<uint32_t>(nblk);
     g.total = c.take<uint32_t>(32);
+    g.gs = SortBufs<uint32_t>::carve(c, P);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return g;
   }
@@ -174,50 +206,21 @@ struct BinKeep {
   }
 };
 
-// Radix sort geometry (see sort.cu).
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
-constexpr int SORT_MAX_PASSES = 8;
-
-// Ping-pong buffers + look-back state of one radix sort of n (key, value) pairs.
-template <typename K>
-struct SortBufs {
-  K* keys[2];
-  uint32_t* vals[2];
-  uint32_t* hist;     // [SORT_MAX_PASSES][256] global digit histograms -> exclusive bases
-  uint32_t* ticket;   // [SORT_MAX_PASSES] dynamic tile id counters
-  uint32_t* status;   // [passes][ntiles][256] decoupled look-back words
-  size_t status_words;
-  static SortBufs carve(Carver& c, int64_t n) {
-    SortBufs b;
-    int64_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
-    b.keys[0] = c.take<K>(n + 1);
-    b.keys[1] = c.take<K>(n + 1);
-    b.vals[0] = c.take<uint32_t>(n + 1);
-    b.vals[1] = c.take<uint32_t>(n + 1);
-    b.hist = c.take<uint32_t>(SORT_MAX_PASSES * 256);
-    b.ticket = c.take<uint32_t>(32);
-    b.status_words = size_t(sizeof(K)) * size_t(ntiles > 0 ? ntiles : 1) * 256;   // sizeof(K) = max passes
-    b.status = c.take<uint32_t>(b.status_words);
-    return b;
-  }
-};
-
-// Forward-only scratch of the binning step.
-//   gs: the P Gaussians sorted by the bits of their view-space depth (value = Gaussian index)
-//   is: the R tile-instances, emitted in that depth order, sorted by tile index only
+// Binning sorts twice:
+//   GeomState::gs: the P Gaussians sorted by the bits of their view-space depth (value = Gaussian index);
+//                  runs inside cg_raster_fwd_geom, overlapping the host's wait for R
+//   BinScratch::is (forward-only scratch): the R tile-instances, emitted in that depth order, sorted by
+//                  tile index only
 // A stable sort by tile of a list that is already in (depth, index) order is the
 // (tile, depth) order with ties in emission = index order, i.e. exactly the permutation the
 // reference gets from one 64-bit sort of tile<<32|depth (rasterizer_impl.cu:70-111, :309-314),
 // but the big R-sized passes shrink from 6 x 24 B to 2 x 16 B per instance.
 struct BinScratch {
-  SortBufs<uint32_t> gs;
   SortBufs<uint32_t> is;
   static BinScratch carve(void* base, int64_t P, int64_t R, size_t* bytes) {
+    (void)P;
     Carver c(base);
     BinScratch b;
-    b.gs = SortBufs<uint32_t>::carve(c, P);
     b.is = SortBufs<uint32_t>::carve(c, R);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
@@ -238,5 +241,7 @@ inline uint32_t tile_key_bits(uint32_t n) {
 // two ping-pong buffers holds the result. Instantiated for uint32_t and uint64_t keys (sort.cu).
 template <typename K>
 int radix_sort_pairs(const SortBufs<K>& b, int64_t n, int end_bit, int* out_buf, bool debug, cudaStream_t stream);
+// Which ping-pong buffer radix_sort_pairs leaves the result in (number of digit passes is ceil(end_bit / 8)).
+inline int radix_sort_result_buf(int end_bit) { int p = (end_bit + 7) / 8; return (p < 1 ? 1 : p) & 1; }
 
 }  // namespace cg

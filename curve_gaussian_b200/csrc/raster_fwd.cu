@@ -467,10 +467,34 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   { StageTimer t_(ST_SCAN, st, 1);
   scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
   CG_LAUNCH_CHECK(s->debug, st);
-  uint32_t total = 0;
-  CG_CUDA(cudaMemcpyAsync(&total, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  CG_CUDA(cudaStreamSynchronize(st));
-  *num_rendered = int64_t(total);
+  // R goes to pinned host memory; the host then waits on an EVENT recorded right behind that copy while the
+  // stream already carries the next, R-independent stage (depth sort of the Gaussians + offsets in depth
+  // order), so the wake-up latency of the host is hidden behind ~0.1 ms of useful GPU work.
+  int dev = 0;
+  CG_CUDA(cudaGetDevice(&dev));
+  static thread_local uint32_t* h_total[64] = {nullptr};
+  static thread_local cudaEvent_t h_event[64] = {nullptr};
+  CG_ARG(dev >= 0 && dev < 64, "device ordinal");
+  if (!h_total[dev]) {
+    CG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_total[dev]), 64, cudaHostAllocDefault));
+    CG_CUDA(cudaEventCreateWithFlags(&h_event[dev], cudaEventDisableTiming));
+  }
+  CG_CUDA(cudaMemcpyAsync(h_total[dev], g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CG_CUDA(cudaEventRecord(h_event[dev], st));
+  {
+    int rc, gcur = 0;
+    { StageTimer t_(ST_SORT, st, 1);
+    init_depth_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, g.gs.keys[0], g.gs.vals[0]);
+    CG_LAUNCH_CHECK(s->debug, st);
+    rc = radix_sort_pairs<uint32_t>(g.gs, P, 32, &gcur, s->debug != 0, st); }
+    if (rc != CG_OK) return rc;
+    { StageTimer t_(ST_SCAN, st, 2);
+    perm_block_sums<<<unsigned(nblk), 256, 0, st>>>(P, g.gs.vals[gcur], g);
+    scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
+    CG_LAUNCH_CHECK(s->debug, st);
+  }
+  CG_CUDA(cudaEventSynchronize(h_event[dev]));
+  *num_rendered = int64_t(*h_total[dev]);
   return CG_OK;
 }
 
@@ -489,23 +513,13 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
   CG_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), st));
   if (R > 0) {
     int rc;
-    // 1. Gaussians by depth (P pairs, 4 digit passes over 8 B pairs)
-    int gcur = 0;
-    { StageTimer t_(ST_SORT, st, 1);
-    init_depth_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, bs.gs.keys[0], bs.gs.vals[0]);
-    CG_LAUNCH_CHECK(s->debug, st);
-    rc = radix_sort_pairs<uint32_t>(bs.gs, P, 32, &gcur, s->debug != 0, st); }
-    if (rc != CG_OK) return rc;
-    const uint32_t* perm = bs.gs.vals[gcur];
-    // 2. offsets in depth order, then one (tile, Gaussian) pair per overlapped tile
-    { StageTimer t_(ST_SCAN, st, 2);
-    perm_block_sums<<<unsigned(nblk), 256, 0, st>>>(P, perm, g);
-    scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
-    CG_LAUNCH_CHECK(s->debug, st);
+    // the Gaussians were depth-sorted and their offsets scanned in that order by cg_raster_fwd_geom;
+    // here: one (tile, Gaussian) pair per overlapped tile
+    const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];
     { StageTimer t_(ST_EMIT_KEYS, st, 1);
     emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, perm, g, gx, bs.is.keys[0], bs.is.vals[0]); }
     CG_LAUNCH_CHECK(s->debug, st);
-    // 3. stable sort by tile only
+    // stable sort by tile only
     int cur = 0;
     const int end_bit = int(tile_key_bits(uint32_t(tiles)));
     { StageTimer t_(ST_SORT, st, 0);

@@ -77,17 +77,19 @@ typedef struct cg_raster_settings {
 /* Sizes of the opaque state buffers the caller must allocate (bytes).
  * geom: per-Gaussian state, img: per-pixel/per-tile state, both saved for
  * backward. bin_keep: sorted per-instance records + point list, saved for
- * backward. bin_scratch: sort double buffers (P Gaussians by depth, R instances
- * by tile), only live during forward. */
+ * backward (geom also holds the depth-sort buffers of the P Gaussians).
+ * bin_scratch: sort double buffers of the R instances, only live during forward. */
 size_t cg_raster_geom_bytes(int64_t P);
 size_t cg_raster_img_bytes(int32_t W, int32_t H);
 size_t cg_raster_bin_keep_bytes(int64_t R);
 size_t cg_raster_bin_scratch_bytes(int64_t P, int64_t R);
 
-/* Forward, stage 1: per-Gaussian EWA projection + tile counts + prefix scan.
- * Writes radii[P] (int32) and the geom state; returns the number of
- * tile-instances R through *num_rendered (host int; this call synchronizes
- * the stream for that 4-byte read, as rasterizer_impl.cu:287 does).
+/* Forward, stage 1: per-Gaussian EWA projection + tile counts + prefix scan, then the
+ * depth sort of the Gaussians and their offsets in depth order (both independent of R).
+ * Writes radii[P] (int32) and the geom state; returns the number of tile-instances R
+ * through *num_rendered (host int). Like rasterizer_impl.cu:287 this call waits for that
+ * 4-byte read, but on an event recorded right behind the copy, so the depth sort keeps
+ * the GPU busy while the host wakes up and allocates the R-sized buffers.
  * Exactly one of (scales+rotations) / cov3D_precomp must be non-NULL. */
 int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P,
                        const float* means3D,      /* (P,3) */

@@ -40,7 +40,8 @@ def test_size_queries():
     assert 0 < a < b and a % 128 == 0
     assert lib.cg_raster_img_bytes(1920, 1080) >= 1920 * 1080 * 8
     assert lib.cg_raster_bin_keep_bytes(1000) >= 1000 * 52
-    assert lib.cg_raster_bin_scratch_bytes(100, 1000) >= 1000 * 16 + 100 * 16
+    assert lib.cg_raster_bin_scratch_bytes(100, 1000) >= 1000 * 16
+    assert lib.cg_raster_geom_bytes(1000) >= 1000 * (40 + 16)   # per-Gaussian state + the depth-sort buffers
     assert lib.cg_raster_bwd_scratch_bytes(10) == 320
     assert lib.cg_sample_scratch_bytes(10, 12) >= 32
     assert lib.cg_knn_scratch_bytes(3375) > 0
