@@ -77,7 +77,7 @@ if os.path.exists(rep):
         for r in rows[2:]:
             d = dict(zip(hdr, r))
             kn = d["Kernel Name"]
-            base = kn.split("(")[0].split("::")[-1].split("<")[0].strip()
+            base = kn.split("(")[0].split("<")[0].split("::")[-1].split()[-1].strip()
             seen[base] += 1
             f.write(f"{kn[:110]}   grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
             for w in want:
