@@ -112,6 +112,35 @@ def profile_read() -> dict:
     return out
 
 
+class _NullContext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullContext()
+
+
+def on_device(dev):
+    """Context manager making `dev` the current CUDA device; free when it already is (the common case)."""
+    import torch
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(idx)
+
+
+def stream(dev) -> int:
+    """Raw cudaStream_t of torch's current stream on `dev` (what every cg_* call takes as `void* stream`)."""
+    import torch
+    idx = dev.index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().cg_last_error().decode("utf-8", "replace")

@@ -29,11 +29,11 @@ class _CurveActivate(torch.autograd.Function):
         opacity = torch.empty((P, 1), dtype=torch.float32, device=dev)
         scales = torch.empty((P, 3), dtype=torch.float32, device=dev)
         all_map = torch.empty((P, 4), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.cg_activate_fwd(B, n, _lib.ptr(xyz_), _lib.ptr(rot_), _lib.ptr(scal_), _lib.ptr(ol_),
                                            _lib.ptr(ml_), float(mask_thr), _lib.ptr(cam_), _lib.ptr(vm_),
                                            _lib.ptr(rot_n), _lib.ptr(opacity), _lib.ptr(scales), _lib.ptr(all_map),
-                                           torch.cuda.current_stream(dev).cuda_stream), "cg_activate_fwd")
+                                           _lib.stream(dev)), "cg_activate_fwd")
         ctx.save_for_backward(xyz_, rot_, scal_, ol_, ml_ if ml_ is not None else torch.empty(0, device=dev), cam_, vm_)
         ctx.meta = (B, n, float(mask_thr), tuple(opacity_logit.shape),
                     tuple(mask_logit.shape) if mask_logit is not None else None)
@@ -53,12 +53,12 @@ class _CurveActivate(torch.autograd.Function):
         g_scaling = torch.empty((P, 3), dtype=torch.float32, device=dev)
         g_ol = torch.empty((B,), dtype=torch.float32, device=dev)
         g_ml = torch.empty((P,), dtype=torch.float32, device=dev) if ml_shape is not None else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.cg_activate_bwd(B, n, _lib.ptr(xyz_), _lib.ptr(rot_), _lib.ptr(scal_), _lib.ptr(ol_),
                                            _lib.ptr(ml_) if ml_shape is not None else None, thr, _lib.ptr(cam_),
                                            _lib.ptr(vm_), _lib.ptr(g_rot_n), _lib.ptr(g_opacity), _lib.ptr(g_scales),
                                            _lib.ptr(g_all_map), _lib.ptr(g_rot), _lib.ptr(g_scaling), _lib.ptr(g_ol),
-                                           _lib.ptr(g_ml), torch.cuda.current_stream(dev).cuda_stream),
+                                           _lib.ptr(g_ml), _lib.stream(dev)),
                        "cg_activate_bwd")
         return (None, g_rot, g_scaling, g_ol.view(ol_shape), g_ml.view(ml_shape) if g_ml is not None else None,
                 None, None, None, None)

@@ -16,7 +16,7 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
     if P == 0:
         return out
     scratch = torch.empty(lib.cg_knn_scratch_bytes(P), dtype=torch.uint8, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _lib.on_device(pts.device):
         _lib.check(lib.cg_knn_mean_dist2(P, pts.data_ptr(), out.data_ptr(), scratch.data_ptr(),
-                                         torch.cuda.current_stream(pts.device).cuda_stream), "cg_knn_mean_dist2")
+                                         _lib.stream(pts.device)), "cg_knn_mean_dist2")
     return out

@@ -45,11 +45,11 @@ class _EdgeSSIMLoss(torch.autograd.Function):
         d1 = torch.empty_like(a) if train else None
         d2 = torch.empty_like(a) if train else None
         d3 = torch.empty_like(a) if train else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.cg_edge_ssim_loss_fwd(H, W, a.data_ptr(), b.data_ptr(), float(threshold), float(lambda_mse),
                                                  float(lambda_dssim), 0.01 ** 2, 0.03 ** 2, stats.data_ptr(),
                                                  loss.data_ptr(), _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(d3),
-                                                 torch.cuda.current_stream(dev).cuda_stream), "cg_edge_ssim_loss_fwd")
+                                                 _lib.stream(dev)), "cg_edge_ssim_loss_fwd")
         if train:
             ctx.save_for_backward(a, b, stats, d1, d2, d3)
         ctx.meta = (H, W, float(threshold), float(lambda_mse), float(lambda_dssim), tuple(image.shape))
@@ -62,10 +62,10 @@ class _EdgeSSIMLoss(torch.autograd.Function):
         H, W, thr, lm, ld, shape = ctx.meta
         out = torch.empty_like(a)
         g = g.float().contiguous()
-        with torch.cuda.device(a.device):
+        with _lib.on_device(a.device):
             _lib.check(lib.cg_edge_ssim_loss_bwd(H, W, a.data_ptr(), b.data_ptr(), thr, lm, ld, stats.data_ptr(),
                                                  g.data_ptr(), d1.data_ptr(), d2.data_ptr(), d3.data_ptr(),
-                                                 out.data_ptr(), torch.cuda.current_stream(a.device).cuda_stream),
+                                                 out.data_ptr(), _lib.stream(a.device)),
                        "cg_edge_ssim_loss_bwd")
         return out.view(shape), None, None, None, None
 
@@ -90,9 +90,9 @@ class _RotateChannels(torch.autograd.Function):
             mm = mm.contiguous()
         n = x.shape[-1] * x.shape[-2]
         out = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _lib.check(lib.cg_rotate_channels(n, x.data_ptr(), mm.data_ptr(), int(mm.stride(0)), 0, out.data_ptr(),
-                                              torch.cuda.current_stream(x.device).cuda_stream), "cg_rotate_channels")
+                                              _lib.stream(x.device)), "cg_rotate_channels")
         ctx.save_for_backward(mm)
         return out
 
@@ -103,9 +103,9 @@ class _RotateChannels(torch.autograd.Function):
         g = g.float().contiguous()
         n = g.shape[-1] * g.shape[-2]
         out = torch.empty_like(g)
-        with torch.cuda.device(g.device):
+        with _lib.on_device(g.device):
             _lib.check(lib.cg_rotate_channels(n, g.data_ptr(), mm.data_ptr(), int(mm.stride(0)), 1, out.data_ptr(),
-                                              torch.cuda.current_stream(g.device).cuda_stream), "cg_rotate_channels")
+                                              _lib.stream(g.device)), "cg_rotate_channels")
         return out, None
 
 

@@ -88,7 +88,7 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
         return 0, z(1, H, W), torch.zeros(0, dtype=torch.int32, device=dev), e, e, e, z(1, H, W), z(4, H, W)
     keep: list = []
     s = _settings_struct(rs, keep)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    stream = _lib.stream(dev)
 
     color = torch.empty((1, H, W), dtype=torch.float32, device=dev)
     invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
@@ -109,7 +109,7 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
         raise _lib.CurveGSError("colors_precomp is required (the SH path is not part of the curve pipeline)")
 
     R = C.c_int64(0)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.cg_raster_fwd_geom(C.byref(s), P, _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales),
                                           _lib.ptr(rotations), _lib.ptr(cov3D), _lib.ptr(radii), geom.data_ptr(),
                                           geom.numel(), C.byref(R), stream), "cg_raster_fwd_geom")
@@ -127,11 +127,13 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
 
 
 def rasterize_backward_raw(rs, means3D, radii, colors_precomp, all_maps, opacities, scales, rotations,
-                           cov3Ds_precomp, grad_color, grad_invdepth, grad_all_map, geom, R, bin_keep, img):
+                           cov3Ds_precomp, grad_color, grad_invdepth, grad_all_map, geom, R, bin_keep, img,
+                           need_cov3D=True, need_all_map=True):
     """The `_C.rasterize_gaussians_backward` equivalent (rasterize_points.cu:133-240).
 
     Returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
-    dL_drotations, dL_dall_map).
+    dL_drotations, dL_dall_map). With need_cov3D / need_all_map False the corresponding entry is None and
+    is neither allocated nor written (the autograd wrapper asks only for what autograd will use).
     """
     lib = _lib.load()
     dev = means3D.device
@@ -142,16 +144,16 @@ def rasterize_backward_raw(rs, means3D, radii, colors_precomp, all_maps, opaciti
         return z(0, 3), z(0, 1), z(0, 1), z(0, 3), z(0, 6), z(0, 0, 3), z(0, 3), z(0, 4), z(0, 4)
     keep: list = []
     s = _settings_struct(rs, keep)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    stream = _lib.stream(dev)
     d_means2D = torch.empty((P, 3), **f)
     d_colors = torch.empty((P, 1), **f)
     d_opacity = torch.empty((P, 1), **f)
     d_means3D = torch.empty((P, 3), **f)
-    d_cov3D = torch.empty((P, 6), **f)
+    d_cov3D = torch.empty((P, 6), **f) if need_cov3D else None
     d_sh = torch.zeros((P, 0, 3), **f)
     d_scales = torch.empty((P, 3), **f)
     d_rot = torch.empty((P, 4), **f)
-    d_all_map = torch.empty((P, 4), **f)
+    d_all_map = torch.empty((P, 4), **f) if need_all_map else None
     scratch = _bytes(lib.cg_raster_bwd_scratch_bytes(P), dev)
 
     means3D = _f32c(means3D)
@@ -165,13 +167,13 @@ def rasterize_backward_raw(rs, means3D, radii, colors_precomp, all_maps, opaciti
     g_color = _f32c(grad_color)
     g_invd = _f32c(grad_invdepth) if grad_invdepth is not None and grad_invdepth.numel() else None
     g_map = _f32c(grad_all_map) if grad_all_map is not None and grad_all_map.numel() else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.cg_raster_bwd(C.byref(s), P, int(R), _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales),
                                      _lib.ptr(rotations), _lib.ptr(cov3D), _lib.ptr(radii), geom.data_ptr(),
                                      img.data_ptr(), bin_keep.data_ptr(), g_color.data_ptr(), _lib.ptr(g_invd),
                                      _lib.ptr(g_map), scratch.data_ptr(), d_means2D.data_ptr(), d_colors.data_ptr(),
-                                     d_opacity.data_ptr(), d_means3D.data_ptr(), d_cov3D.data_ptr(),
-                                     d_scales.data_ptr(), d_rot.data_ptr(), d_all_map.data_ptr(), stream),
+                                     d_opacity.data_ptr(), d_means3D.data_ptr(), _lib.ptr(d_cov3D),
+                                     d_scales.data_ptr(), d_rot.data_ptr(), _lib.ptr(d_all_map), stream),
                    "cg_raster_bwd")
     return d_means2D, d_colors, d_opacity, d_means3D, d_cov3D, d_sh, d_scales, d_rot, d_all_map
 
@@ -183,9 +185,9 @@ def mark_visible(positions, viewmatrix, projmatrix):
     if P:
         positions = _f32c(positions)
         vm, pm = _f32c(viewmatrix), _f32c(projmatrix)
-        with torch.cuda.device(positions.device):
+        with _lib.on_device(positions.device):
             _lib.check(lib.cg_mark_visible(P, positions.data_ptr(), vm.data_ptr(), pm.data_ptr(), present.data_ptr(),
-                                           torch.cuda.current_stream(positions.device).cuda_stream), "cg_mark_visible")
+                                           _lib.stream(positions.device)), "cg_mark_visible")
     return present
 
 
@@ -223,12 +225,15 @@ class _RasterizeGaussians(torch.autograd.Function):
                                          device=means3D.device)
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_all_map) = rasterize_backward_raw(
             rs, means3D, radii, colors_precomp, all_maps, opacities, scales, rotations, cov3Ds_precomp,
-            grad_out_color, grad_out_depth, grad_out_all_map, geom, ctx.num_rendered, bin_keep, img)
+            grad_out_color, grad_out_depth, grad_out_all_map, geom, ctx.num_rendered, bin_keep, img,
+            need_cov3D=cov3Ds_precomp is not None and cov3Ds_precomp.numel() > 0,
+            # no upstream gradient on the all_map image -> dL/dall_map is identically zero: hand autograd None
+            need_all_map=grad_out_all_map is not None and all_maps is not None and all_maps.numel() > 0)
         if opacities.dim() == 1:
             g_opac = g_opac.view(-1)
 
         def like(g, t):
-            if t is None or t.numel() == 0:
+            if g is None or t is None or t.numel() == 0:
                 return None
             return g.view(t.shape) if g.numel() == t.numel() else g
 

@@ -38,10 +38,10 @@ class _CurveSample(torch.autograd.Function):
         norms = torch.empty(2, dtype=torch.float32, device=dev)
         scratch = torch.empty(128, dtype=torch.uint8, device=dev)   # the forward only needs the 64-byte sums block
         half_step = 0.5 / n
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.cg_sample_fwd(B, n, _lib.ptr(cp), _lib.ptr(w), _lib.ptr(isb), _lib.ptr(tt), half_step,
                                          _lib.ptr(xyz), _lib.ptr(rot), _lib.ptr(scaling), norms.data_ptr(),
-                                         scratch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                                         scratch.data_ptr(), _lib.stream(dev)),
                        "cg_sample_fwd")
         ctx.save_for_backward(cp, w, isb if isb is not None else torch.empty(0, device=dev), tt, norms)
         ctx.shape = (B, n, half_step, tuple(width.shape))
@@ -59,11 +59,11 @@ class _CurveSample(torch.autograd.Function):
         scratch = torch.empty(max(lib.cg_sample_scratch_bytes(B, n), 8), dtype=torch.uint8, device=dev)
         c = lambda g: None if g is None else g.float().contiguous()
         g_xyz, g_rot, g_scaling = c(g_xyz), c(g_rot), c(g_scaling)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.cg_sample_bwd(B, n, _lib.ptr(cp), _lib.ptr(w), _lib.ptr(isb), _lib.ptr(tt), half_step,
                                          norms.data_ptr(), _lib.ptr(g_xyz), _lib.ptr(g_rot), _lib.ptr(g_scaling),
                                          _lib.ptr(g_cp), _lib.ptr(g_w), scratch.data_ptr(),
-                                         torch.cuda.current_stream(dev).cuda_stream), "cg_sample_bwd")
+                                         _lib.stream(dev)), "cg_sample_bwd")
         return g_cp, g_w.view(wshape), None, None
 
 

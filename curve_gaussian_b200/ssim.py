@@ -19,10 +19,10 @@ def _fusedssim(C1, C2, img1, img2, train):
     d1 = torch.empty_like(a) if train else None
     d2 = torch.empty_like(a) if train else None
     d3 = torch.empty_like(a) if train else None
-    with torch.cuda.device(a.device):
+    with _lib.on_device(a.device):
         _lib.check(lib.cg_ssim_fwd(B, CH, H, W, float(C1), float(C2), _lib.ptr(a), _lib.ptr(b), _lib.ptr(m),
                                    _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(d3),
-                                   torch.cuda.current_stream(a.device).cuda_stream), "cg_ssim_fwd")
+                                   _lib.stream(a.device)), "cg_ssim_fwd")
     e = torch.empty(0)
     return m, (d1 if train else e), (d2 if train else e), (d3 if train else e)
 
@@ -34,10 +34,10 @@ def _fusedssim_backward(C1, C2, img1, img2, dL_dmap, d1, d2, d3):
     g = dL_dmap.float().contiguous()
     B, CH, H, W = a.shape
     out = torch.empty_like(a)
-    with torch.cuda.device(a.device):
+    with _lib.on_device(a.device):
         _lib.check(lib.cg_ssim_bwd(B, CH, H, W, float(C1), float(C2), _lib.ptr(a), _lib.ptr(b), _lib.ptr(g),
                                    _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(d3), _lib.ptr(out),
-                                   torch.cuda.current_stream(a.device).cuda_stream), "cg_ssim_bwd")
+                                   _lib.stream(a.device)), "cg_ssim_bwd")
     return out
 
 

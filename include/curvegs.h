@@ -118,7 +118,8 @@ int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R,
  * rasterize_points.cu:173-193: dL_dmeans2D (P,3), dL_dcolors (P,1),
  * dL_dopacity (P,1), dL_dmeans3D (P,3), dL_dcov3D (P,6), dL_dscales (P,3),
  * dL_drotations (P,4), dL_dall_map (P,4). The caller need not zero them.
- * grad_scratch must hold cg_raster_bwd_scratch_bytes(P). */
+ * dL_dcov3D and dL_dall_map_in may be NULL when the caller has no use for them
+ * (they are then not written). grad_scratch must hold cg_raster_bwd_scratch_bytes(P). */
 size_t cg_raster_bwd_scratch_bytes(int64_t P);
 int cg_raster_bwd(const cg_raster_settings* s, int64_t P, int64_t R,
                   const float* means3D, const float* opacities, const float* scales,
