@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcurvegs.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class RasterSettings(C.Structure):
@@ -70,6 +70,12 @@ SIGNATURES = {
     "cg_edge_ssim_loss_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_edge_ssim_loss_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_rotate_channels": (C.c_int, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "cg_curve_smooth_scratch_bytes": (_sz, []),
+    "cg_curve_smooth_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp]),
+    "cg_curve_smooth_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp]),
+    "cg_endpoint_conn_scratch_bytes": (_sz, [_i64]),
+    "cg_endpoint_conn_fwd": (C.c_int, [_i64, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "cg_endpoint_conn_bwd": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "cg_knn_scratch_bytes": (_sz, [_i64]),
     "cg_knn_mean_dist2": (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
 }

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcurvegs.so")
 OBJDIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "sort.cu", "raster_fwd.cu", "raster_bwd.cu", "sample.cu", "activate.cu", "ssim.cu", "knn.cu", "loss.cu"]
+SOURCES = ["api.cu", "sort.cu", "raster_fwd.cu", "raster_bwd.cu", "sample.cu", "activate.cu", "ssim.cu", "knn.cu", "loss.cu", "reg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

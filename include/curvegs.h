@@ -18,6 +18,8 @@
  *                         (scene/gaussian_curve_model.py:70-89,180-198; utils/general_utils.py:9-86)
  *   cg_ssim_*          -> fused_ssim_cuda.fusedssim / fusedssim_backward (fused-ssim/ssim.cu:368-444)
  *   cg_knn_mean_dist2  -> simple_knn._C.distCUDA2 (simple-knn/spatial.cu:15-26, simple_knn.cu:186-222)
+ *   cg_edge_ssim_loss_*, cg_curve_smooth_*, cg_endpoint_conn_* -> the caller's per-iteration loss terms
+ *                         (train.py:101-107, :119-124, :133-146), optional fused forms
  *
  * All float tensors are fp32, contiguous row-major; "absent" tensors are NULL.
  */
@@ -235,6 +237,35 @@ int cg_edge_ssim_loss_bwd(int32_t H, int32_t W, const float* img, const float* g
  * (gaussian_renderer/__init__.py:144), a (H*W,3)x(3,3) GEMM in the reference. */
 int cg_rotate_channels(int64_t n, const float* in, const float* m3x3, int32_t ld, int32_t transpose,
                        float* out, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Curve-side regularisers of the training step (reference caller: train.py) */
+/* ------------------------------------------------------------------ */
+
+/* Curve smoothness (train.py:119-124): mean over the B*(n-1) adjacent sample pairs of
+ * 1 - |cos(dir[b,m], dir[b,m+1])|, dir = first column of
+ * quaternion_to_matrix(normalize(rotation)) (gaussian_curve_model.py:95-97,120-122).
+ * rotation is the RAW (P,4) quaternion of the curve model; the backward returns the
+ * gradient with respect to it. loss_out / g_loss are DEVICE scalars (g_loss NULL = 1).
+ * scratch: cg_curve_smooth_scratch_bytes() bytes, 8-byte aligned. */
+size_t cg_curve_smooth_scratch_bytes(void);
+int cg_curve_smooth_fwd(int64_t B, int32_t n, const float* rotation, void* scratch, float* loss_out, void* stream);
+int cg_curve_smooth_bwd(int64_t B, int32_t n, const float* rotation, const float* g_loss, float* g_rotation,
+                        void* stream);
+
+/* Endpoint connectivity (train.py:133-146): over the 2B curve endpoints (first and last
+ * control point of every curve), the mean Euclidean distance of all ordered pairs closer
+ * than dis_thr, excluding pairs of endpoints of the same curve; 0 when there is none (the
+ * reference then skips the term). The reference builds torch.cdist's dense (2B)^2 matrix;
+ * here the pairs are streamed. curve_points is (B,4,3). The forward also writes v (2B,3),
+ * the per-endpoint sum of unit difference vectors, which the backward scales into
+ * g_curve_points (B,4,3) (rows 1 and 2 are written as zeros). scratch:
+ * cg_endpoint_conn_scratch_bytes(B), 8-byte aligned, kept for the backward. */
+size_t cg_endpoint_conn_scratch_bytes(int64_t B);
+int cg_endpoint_conn_fwd(int64_t B, const float* curve_points, float dis_thr, void* scratch, float* v,
+                         float* loss_out, void* stream);
+int cg_endpoint_conn_bwd(int64_t B, const float* v, const void* scratch, const float* g_loss,
+                         float* g_curve_points, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* simple-knn (reference: submodules/simple-knn)                        */

@@ -120,3 +120,28 @@ def raster_inputs(xyz, rotation, scaling, opacity_logit, n, mask_logit, cam_cent
     all_map = torch.cat([local, torch.ones_like(local[:, :1])], dim=1)
     colors = torch.ones(xyz.shape[0], 1, device=xyz.device)
     return xyz, opacity, scales, rot_n, colors, all_map
+
+
+def curve_smoothness(rotation, n):
+    """train.py:119-124 restated: dir = first column of quaternion_to_matrix(F.normalize(_rotation))
+    (scene/gaussian_curve_model.py:95-97,120-122), 1 - |cosine similarity| of adjacent samples, mean."""
+    q = torch.nn.functional.normalize(rotation)
+    dir_global = quaternion_to_matrix(q)[..., 0].view(-1, n, 3)
+    cos_sim = 1 - torch.nn.functional.cosine_similarity(dir_global[:, :-1, :], dir_global[:, 1:, :], dim=-1).abs()
+    return cos_sim.mean()
+
+
+def endpoint_connectivity(curve_points, dis_thr=0.05):
+    """train.py:133-146 restated (exact-difference distances; torch.cdist's matmul shortcut is an fp32
+    approximation of the same quantity). Returns 0 where the reference skips the term (no valid pair)."""
+    start_points, end_points = curve_points[:, 0], curve_points[:, -1]
+    all_points = torch.cat([start_points, end_points], dim=0)
+    B = start_points.shape[0]
+    mask = torch.eye(B, dtype=torch.bool, device=curve_points.device)
+    mask = torch.cat([torch.cat([mask, mask], dim=1), torch.cat([mask, mask], dim=1)], dim=0)
+    dist = torch.cdist(all_points, all_points, p=2, compute_mode="donot_use_mm_for_euclid_dist")
+    with torch.no_grad():
+        valid_mask = (dist < dis_thr) & (~mask)
+    if valid_mask.any():
+        return dist[valid_mask].mean()
+    return curve_points.sum() * 0.0
