@@ -57,7 +57,7 @@ def config_dict(a, extra=None):
          "image": f"{a.width}x{a.height}", "step": "1 view/rank: sample -> render -> edge+SSIM loss -> backward",
          "loss": "unfused (torch edge_aware_loss + fused_ssim)" if a.unfused_loss else "fused edge+SSIM loss op",
          "l2": "per-step working set (~0.9 GB of sorted records + keys) exceeds the 126 MB L2; no flush needed",
-         "parallelism": f"views sharded over {a.gpus} rank(s), one all-reduce of the flat curve gradient per step"}
+         "parallelism": f"views sharded over {a.gpus} rank(s) (cost-balanced groups), one all-reduce of the flat curve gradient per step"}
     if extra:
         c.update(extra)
     return c
@@ -159,7 +159,20 @@ def run_ours(a):
     bg = torch.zeros(3, device=dev)
     pipe = Pipe()
     nviews = max(1, min(a.views, a.steps + a.warmup))
-    cams = [c.to(dev) for c in synth.random_cameras(nviews * world, W, H, seed=0)[rank::world]]
+    all_cams = synth.random_cameras(nviews * world, W, H, seed=0)
+    if world > 1:
+        # every step ends with an all-reduce, so it lasts as long as its most expensive view: group views of
+        # similar cost (tile-instance count R, measured once, identically on every rank) into the same step
+        from curve_gaussian_b200 import rasterizer as _rz
+        from curve_gaussian_b200.parallel import balanced_view_groups
+        costs = []
+        with torch.no_grad():
+            for c in all_cams:
+                render(c.to(dev), model, pipe, bg)
+                costs.append(_rz.rasterize_forward_raw.last_R)
+        cams = [all_cams[g[rank]].to(dev) for g in balanced_view_groups(costs, world)]
+    else:
+        cams = [c.to(dev) for c in all_cams]
 
     # ground-truth edge maps: the same curves with control points perturbed by N(0, 0.01^2) (SURVEY 8d ii)
     g = torch.Generator().manual_seed(123)

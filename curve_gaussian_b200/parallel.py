@@ -20,6 +20,21 @@ def shard_views(views: Sequence, rank: int, world: int) -> List:
     return list(views[rank::world])
 
 
+def balanced_view_groups(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Group view indices so that the `world` views rendered in the same step cost about the same.
+
+    Every step ends with an all-reduce, so a step takes as long as its most expensive view; with views of
+    uneven cost (the number of tile-instances R varies by tens of percent between cameras) round-robin
+    sharding pays max-over-ranks every step. Sorting by cost and cutting the sorted list into consecutive
+    groups of `world` makes the members of a group near-equal. Returns groups[s][r] = index of the view rank r
+    renders in step s; views that do not fill a last complete group are dropped (as round-robin would leave
+    some ranks idle there)."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    return [order[s * world:(s + 1) * world] for s in range(len(order) // world)]
+
+
 class FlatGrad:
     """One contiguous gradient buffer behind several parameters."""
 

@@ -73,3 +73,16 @@ def test_flat_grad_views_accumulate_in_place():
     assert fg.flat.abs().sum() > 0
     fg.zero()
     assert params[3].grad.abs().sum() == 0
+
+
+def test_balanced_view_groups():
+    from curve_gaussian_b200.parallel import balanced_view_groups
+    costs = [5.0, 1.0, 9.0, 2.0, 8.0, 1.5, 4.0]
+    groups = balanced_view_groups(costs, 2)
+    assert groups == [[2, 4], [0, 6], [3, 5]]                     # sorted by cost, cut in pairs, remainder dropped
+    flat = [i for g in groups for i in g]
+    assert len(set(flat)) == len(flat)
+    # the per-step maximum, summed over steps, never exceeds round-robin's on the same views
+    rr = [costs[i:i + 2] for i in range(0, 6, 2)]
+    assert sum(max(costs[i] for i in g) for g in groups) <= sum(max(g) for g in rr)
+    assert balanced_view_groups(costs, 1) == [[2], [4], [0], [6], [3], [5], [1]]
