@@ -242,13 +242,17 @@ def run_ours(a):
         if host_io:
             k = i % 2
             gt_free[k].record(main)
-            main.wait_event(out_free[k])        # previous D2H out of this staging buffer finished
-            flat_out[k].copy_(flat)             # snapshot: the next step zeroes `flat` while the copy is in flight
+            # every rank reads its loss back; the all-reduced gradient is identical on all ranks, so rank 0 alone
+            # copies it to the host
+            if rank == 0:
+                main.wait_event(out_free[k])    # previous D2H out of this staging buffer finished
+                flat_out[k].copy_(flat)         # snapshot: the next step zeroes `flat` while the copy is in flight
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
-                flat_host2[k].copy_(flat_out[k], non_blocking=True)
+                if rank == 0:
+                    flat_host2[k].copy_(flat_out[k], non_blocking=True)
                 loss_host[i % loss_host.numel()].copy_(loss.detach(), non_blocking=True)
                 out_free[k].record(d2h)
         return loss
@@ -349,7 +353,9 @@ def run_ours(a):
            "clocks": clocks,
            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e / K, 4),
                    "h2d_bytes_per_step": int(gts_host[0].numel() * 4 + 2 * 16 * 4),
-                   "d2h_bytes_per_step": int(flat.numel() * 4 + 4)},
+                   "d2h_bytes_per_step": int(flat.numel() * 4 + 4 * world),
+                   "note": "per step: each rank's edge map host->device; each rank's loss and (rank 0) the all-reduced "
+                           "flat gradient device->host; copies on side streams, double-buffered"},
            "gpu_launches": int(launches),
            "roofline": roofline,
            "stage_ms": {k: round(v, 4) for k, v in sorted(per_stage_step.items(), key=lambda kv: -kv[1])},
