@@ -93,9 +93,28 @@ def make_case(name, dev):
         W, H, P = 128, 128, 4000
         means, scales, rots, opac, colors, amap = synth.random_gaussians(P, seed=4)
         means = means * 6.0 - 2.5   # many behind the camera / far off screen
+    elif name == "ties_and_extremes":
+        # equal sort keys (exact duplicates and a whole plane of Gaussians at one view-space depth), screen-filling
+        # and sub-pixel splats, zero / tiny / saturated opacities, an image that is not a multiple of the tile size
+        W, H, P = 203, 117, 6000
+        means, scales, rots, opac, colors, amap = synth.random_gaussians(P, seed=6)
+        cam0 = synth.random_cameras(1, W, H, seed=15)[0]
+        g = torch.Generator().manual_seed(9)
+        # a plane of constant view-space depth: p = c + a*right + b*up + d*forward with the camera's own axes
+        R_w2c = cam0.world_view_transform[:3, :3]          # columns: camera axes in world coordinates
+        centre = cam0.camera_center
+        ab = (torch.rand(2000, 2, generator=g) - 0.5) * 1.6
+        means[:2000] = centre + ab[:, :1] * R_w2c[:, 0] + ab[:, 1:] * R_w2c[:, 1] + 2.0 * R_w2c[:, 2]
+        means[2000:2500] = means[1500:2000]                 # exact duplicates: ties broken by index only
+        scales[2500:2510] = 3.0                              # screen-filling
+        scales[2510:2600] = 1e-6                             # far below a pixel
+        opac[2600:2700] = 0.0
+        opac[2700:2800] = 1.0 / 255.0
+        opac[2800:2900] = 1.0
+        opac[2900:2950] = 0.003
     else:
         raise KeyError(name)
-    seed = {"cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14}[name]
+    seed = {"cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14, "ties_and_extremes": 15}[name]
     cam = synth.random_cameras(1, W, H, seed=seed)[0].to(dev)
     t = lambda x: x.to(dev).contiguous()
     return cam, t(means), t(scales), t(rots), t(opac), t(colors), t(amap)
@@ -127,7 +146,7 @@ def run_reference(rs, means, colors, opac, scales, rots, amap, grads):
     return out, bw
 
 
-@pytest.mark.parametrize("case", ["cloud_small", "cloud_dense", "discs", "behind_and_offscreen"])
+@pytest.mark.parametrize("case", ["cloud_small", "cloud_dense", "discs", "behind_and_offscreen", "ties_and_extremes"])
 @pytest.mark.parametrize("bg_val", [0.0, 0.3])
 def test_forward_backward_match_reference(cuda_dev, case, bg_val):
     if refload.ref_rasterizer() is None:
