@@ -179,6 +179,7 @@ struct ImgState {
   uint32_t* n_contrib;
   uint2* ranges;
   uint32_t* tile_maxc;  // per tile: max n_contrib over its pixels (backward start)
+  uint32_t* tile_order; // tile ids, longest list first: the launch order of the blend CTAs
   static ImgState carve(void* base, int W, int H, size_t* bytes) {
     Carver c(base);
     ImgState s;
@@ -188,6 +189,7 @@ struct ImgState {
     s.n_contrib = c.take<uint32_t>(npix);
     s.ranges = c.take<uint2>(tiles);
     s.tile_maxc = c.take<uint32_t>(tiles);
+    s.tile_order = c.take<uint32_t>(tiles);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return s;
   }
