@@ -308,13 +308,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr int BATCH = 256;
+constexpr int BATCH = BLEND_THREADS;
 
 // Launch order of the blend CTAs: tiles by descending list length (counting sort on the length quantised to
 // 1024 buckets, one CTA). CTAs are dispatched in index order, so the long tiles start first and the kernel's
 // tail is made of short ones instead of whichever tiles happen to sit in the last image rows.
+// ntiles counts blend CTAs (tile * BLEND_SUBS + sub). Lengths: the tile's range (end - start) when maxc is
+// NULL, else maxc (what the backward walks).
 __global__ void __launch_bounds__(1024)
-order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_order) {
+order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ maxc,
+            uint32_t* __restrict__ tile_order) {
   __shared__ uint32_t s_cnt[1024];
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_max;
@@ -322,15 +325,16 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, uint32_t* __restr
   s_cnt[tid] = 0;
   if (tid == 0) s_max = 1;
   __syncthreads();
+  auto length = [&](uint32_t t) { if (maxc) return maxc[t]; const uint2 r = ranges[t / BLEND_SUBS]; return r.y - r.x; };
   uint32_t mx = 0;
-  for (uint32_t t = tid; t < ntiles; t += 1024) { const uint2 r = ranges[t]; mx = max(mx, r.y - r.x); }
+  for (uint32_t t = tid; t < ntiles; t += 1024) mx = max(mx, length(t));
   mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) atomicMax(&s_max, mx);
   __syncthreads();
   const uint32_t top = s_max;
   // bucket 0 = longest lists
   auto bucket = [&](uint32_t len) { return 1023u - uint32_t((uint64_t(len) * 1023u) / top); };
-  for (uint32_t t = tid; t < ntiles; t += 1024) { const uint2 r = ranges[t]; atomicAdd(&s_cnt[bucket(r.y - r.x)], 1u); }
+  for (uint32_t t = tid; t < ntiles; t += 1024) atomicAdd(&s_cnt[bucket(length(t))], 1u);
   __syncthreads();
   // exclusive scan of the 1024 bucket counts
   const uint32_t v = s_cnt[tid];
@@ -347,19 +351,17 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, uint32_t* __restr
   __syncthreads();
   s_cnt[tid] = s_w[w] + inc - v;   // first output slot of the bucket
   __syncthreads();
-  for (uint32_t t = tid; t < ntiles; t += 1024) {
-    const uint2 r = ranges[t];
-    tile_order[atomicAdd(&s_cnt[bucket(r.y - r.x)], 1u)] = t;   // order inside a bucket is irrelevant
-  }
+  for (uint32_t t = tid; t < ntiles; t += 1024)
+    tile_order[atomicAdd(&s_cnt[bucket(length(t))], 1u)] = t;   // order inside a bucket is irrelevant
 }
 
-// One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block. The tile's
+// BLEND_SUBS CTAs per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block. The tile's
 // sorted records are one contiguous span; thread 0 streams it into a 2-deep shared ring with
 // cp.async.bulk while all threads blend the previous batch. Each warp first tests 32 records
 // at a time (one per lane, block_candidate in common.cuh) against its pixel block and only
 // walks the instances that can reach it, in list order (forward.cu:331-396 semantics).
 template <bool GEO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BLEND_THREADS, 2048 / BLEND_THREADS * 3 / 4)
 blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int grid_x,
           const Rec* __restrict__ rec, int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
@@ -368,11 +370,13 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ uint32_t s_maxc;
 
-  const uint32_t tile = tile_order[blockIdx.x];
+  const uint32_t cta = tile_order[blockIdx.x];
+  const uint32_t tile = cta / BLEND_SUBS, sub = cta % BLEND_SUBS;
   const uint32_t tile_x = tile % uint32_t(grid_x), tile_y = tile / uint32_t(grid_x);
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
-  const uint32_t blk_x = tile_x * TILE_X + (warp & 1) * 8, blk_y = tile_y * TILE_Y + (warp >> 1) * 4;
+  const uint32_t blk_x = tile_x * TILE_X + (warp & 1) * 8;
+  const uint32_t blk_y = tile_y * TILE_Y + sub * BLEND_ROWS + (warp >> 1) * 4;
   const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
   const bool inside = pix_x < uint32_t(W) && pix_y < uint32_t(H);
   const uint32_t pix_id = uint32_t(W) * pix_y + pix_x;
@@ -405,7 +409,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   int todo = total;
   for (int b = 0; b < rounds; ++b, todo -= BATCH) {
     const int num_done = __syncthreads_count(done);
-    if (num_done == TILE_PIX) {
+    if (num_done == BLEND_THREADS) {
       // batch b is (or was) in flight: drain it before the CTA retires
       if (tid == 0) mbar_wait(&s_full[b & 1], (b >> 1) & 1);
       break;
@@ -482,7 +486,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   mc = __reduce_max_sync(0xffffffffu, mc);
   if (lane == 0) atomicMax(&s_maxc, mc);
   __syncthreads();
-  if (tid == 0) tile_maxc[tile] = s_maxc;
+  if (tid == 0) tile_maxc[cta] = s_maxc;
 }
 
 // ---------------------------------------------------------------------------
@@ -576,9 +580,9 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
                                        s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
-  const dim3 grid{unsigned(tiles), 1u, 1u}, block{unsigned(TILE_PIX), 1u, 1u};
-  StageTimer t_blend(ST_BLEND_FWD, st, 2);
-  order_tiles<<<1, 1024, 0, st>>>(uint32_t(tiles), im.ranges, im.tile_order);
+  const dim3 grid{unsigned(tiles) * BLEND_SUBS, 1u, 1u}, block{unsigned(BLEND_THREADS), 1u, 1u};
+  StageTimer t_blend(ST_BLEND_FWD, st, 3);
+  order_tiles<<<1, 1024, 0, st>>>(uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
   CG_LAUNCH_CHECK(s->debug, st);
   if (s->render_geo)
     blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
@@ -586,6 +590,9 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
   else
     blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
                                              out_map, im.final_T, im.n_contrib, im.tile_maxc);
+  CG_LAUNCH_CHECK(s->debug, st);
+  // launch order of the backward CTAs, by the length of list each tile's backward will walk
+  order_tiles<<<1, 1024, 0, st>>>(uint32_t(tiles) * BLEND_SUBS, im.ranges, im.tile_maxc, im.tile_order_bwd);
   CG_LAUNCH_CHECK(s->debug, st);
   return CG_OK;
 }
