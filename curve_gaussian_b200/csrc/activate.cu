@@ -18,6 +18,7 @@ activate_fwd(int64_t P, int n, const float* __restrict__ xyz, const float* __res
              const float* __restrict__ mask_logit, float mask_thr, const float* __restrict__ campos,
              const float* __restrict__ vm, float* __restrict__ rot_n, float* __restrict__ opacity,
              float* __restrict__ scales, float* __restrict__ all_map) {
+  pdl_wait();
   const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (g >= P) return;
   const float4 q = reinterpret_cast<const float4*>(rot)[g];
@@ -53,6 +54,7 @@ activate_bwd_point(int64_t P, int n, const float* __restrict__ xyz, const float*
                    const float* __restrict__ vm, const float* __restrict__ g_rot_n, const float* __restrict__ g_opacity,
                    const float* __restrict__ g_scales, const float* __restrict__ g_all_map,
                    float* __restrict__ g_rot, float* __restrict__ g_scaling, float* __restrict__ g_mask_logit) {
+  pdl_wait();
   const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (g >= P) return;
   // ---- mask / opacity / scales
@@ -110,6 +112,7 @@ activate_bwd_point(int64_t P, int n, const float* __restrict__ xyz, const float*
 __global__ void __launch_bounds__(256)
 activate_bwd_curve(int64_t B, int n, const float* __restrict__ opacity_logit, const float* __restrict__ mask_logit,
                    float mask_thr, const float* __restrict__ g_opacity, float* __restrict__ g_opacity_logit) {
+  pdl_wait();
   const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -149,7 +152,7 @@ int cg_activate_fwd(int64_t B, int32_t n, const float* xyz, const float* rotatio
            reinterpret_cast<uintptr_t>(all_map)) & 15u) == 0, "rotation/rot_n/all_map must be 16-byte aligned");
   const int64_t P = B * n;
   StageTimer t_(ST_ACTIVATE_FWD, st, 1);
-  activate_fwd<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, n, xyz, rotation, scaling, opacity_logit, mask_logit,
+  launch_k(activate_fwd, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, n, xyz, rotation, scaling, opacity_logit, mask_logit,
                                                          mask_thr, campos, viewmatrix, rot_n, opacity, scales, all_map);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
@@ -168,11 +171,11 @@ int cg_activate_bwd(int64_t B, int32_t n, const float* xyz, const float* rotatio
   CG_ARG(!mask_logit || g_mask_logit, "g_mask_logit required with mask_logit");
   const int64_t P = B * n;
   StageTimer t_(ST_ACTIVATE_BWD, st, 2);
-  activate_bwd_point<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, n, xyz, rotation, scaling, opacity_logit, mask_logit,
+  launch_k(activate_bwd_point, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, n, xyz, rotation, scaling, opacity_logit, mask_logit,
                                                                mask_thr, campos, viewmatrix, g_rot_n, g_opacity, g_scales,
                                                                g_all_map, g_rotation, g_scaling, g_mask_logit);
   CG_LAUNCH_CHECK(0, st);
-  activate_bwd_curve<<<unsigned((B * 32 + 255) / 256), 256, 0, st>>>(B, n, opacity_logit, mask_logit, mask_thr,
+  launch_k(activate_bwd_curve, dim3(unsigned((B * 32 + 255) / 256)), dim3(256), 0, st, B, n, opacity_logit, mask_logit, mask_thr,
                                                                     g_opacity, g_opacity_logit);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;

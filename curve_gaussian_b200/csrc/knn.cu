@@ -17,6 +17,7 @@ struct Box { float mnx, mny, mnz, mxx, mxy, mxz; };
 
 __global__ void __launch_bounds__(256)
 knn_bbox(int64_t P, const float* __restrict__ pts, float* __restrict__ bb /*6: min xyz, max xyz as ordered ints*/) {
+  pdl_wait();
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += int64_t(gridDim.x) * blockDim.x)
     for (int k = 0; k < 3; ++k) { const float v = pts[3 * i + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
@@ -49,6 +50,7 @@ __device__ __forceinline__ uint32_t spread10(uint32_t x) {
 __global__ void __launch_bounds__(256)
 knn_morton(int64_t P, const float* __restrict__ pts, const float* __restrict__ bb, uint64_t* __restrict__ keys,
            uint32_t* __restrict__ vals) {
+  pdl_wait();
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= P) return;
   const int* bi = reinterpret_cast<const int*>(bb);
@@ -66,6 +68,7 @@ knn_morton(int64_t P, const float* __restrict__ pts, const float* __restrict__ b
 
 __global__ void __launch_bounds__(BOX)
 knn_boxes(int64_t P, const float* __restrict__ pts, const uint32_t* __restrict__ order, Box* __restrict__ boxes) {
+  pdl_wait();
   __shared__ float red[6][32];
   const int64_t i = int64_t(blockIdx.x) * BOX + threadIdx.x;
   float v[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -114,6 +117,7 @@ __device__ __forceinline__ float box_dist2(const Box& b, float x, float y, float
 __global__ void __launch_bounds__(256)
 knn_search(int64_t P, const float* __restrict__ pts, const uint32_t* __restrict__ order, const Box* __restrict__ boxes,
            float* __restrict__ out) {
+  pdl_wait();
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= P) return;
   const uint32_t me = order[i];
@@ -186,17 +190,17 @@ int cg_knn_mean_dist2(int64_t P, const float* points, float* mean_dist2, void* s
   CG_CUDA(cudaMemcpyAsync(ks.bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
   const int rb = int((P + 255) / 256 < 1184 ? (P + 255) / 256 : 1184);
   StageTimer t_(ST_KNN, st, 4);
-  knn_bbox<<<rb, 256, 0, st>>>(P, points, ks.bb);
+  launch_k(knn_bbox, dim3(rb), dim3(256), 0, st, P, points, ks.bb);
   CG_LAUNCH_CHECK(0, st);
-  knn_morton<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, points, ks.bb, bs.keys[0], bs.vals[0]);
+  launch_k(knn_morton, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, points, ks.bb, bs.keys[0], bs.vals[0]);
   CG_LAUNCH_CHECK(0, st);
   int cur = 0;
   int rc = radix_sort_pairs<uint64_t>(bs, P, 32, &cur, false, st);
   if (rc != CG_OK) return rc;
   const unsigned nbox = unsigned((P + BOX - 1) / BOX);
-  knn_boxes<<<nbox, BOX, 0, st>>>(P, points, bs.vals[cur], ks.boxes);
+  launch_k(knn_boxes, dim3(nbox), dim3(BOX), 0, st, P, points, bs.vals[cur], ks.boxes);
   CG_LAUNCH_CHECK(0, st);
-  knn_search<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, points, bs.vals[cur], ks.boxes, mean_dist2);
+  launch_k(knn_search, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, points, bs.vals[cur], ks.boxes, mean_dist2);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }

@@ -22,6 +22,7 @@ namespace cg {
 __global__ void __launch_bounds__(256)
 rotate_channels_kernel(int64_t n, const float* __restrict__ in, const float* __restrict__ m, int ld, int transpose,
                        float* __restrict__ out) {
+  pdl_wait();
   __shared__ float sm[9];
   if (threadIdx.x < 9) {
     const int c = threadIdx.x / 3, k = threadIdx.x % 3;
@@ -74,7 +75,7 @@ int cg_edge_ssim_loss_fwd(int32_t H, int32_t W, const float* img, const float* g
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS);
   LossParams prm{threshold, lambda_mse, lambda_dssim, C1, C2};
   StageTimer t_(ST_LOSS_FWD, st, 1);
-  ssim_fwd_kernel<true><<<grid, NT, 0, st>>>(H, W, prm, img, gt, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12,
+  launch_k(ssim_fwd_kernel<true>, dim3(grid), dim3(NT), 0, st, H, W, prm, img, gt, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12,
                                             reinterpret_cast<double*>(stats), loss_out);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
@@ -89,7 +90,7 @@ int cg_edge_ssim_loss_bwd(int32_t H, int32_t W, const float* img, const float* g
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS);
   LossParams prm{threshold, lambda_mse, lambda_dssim, 0.f, 0.f};
   StageTimer t_(ST_LOSS_BWD, st, 1);
-  ssim_bwd_kernel<true><<<grid, NT, 0, st>>>(H, W, prm, img, gt, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12,
+  launch_k(ssim_bwd_kernel<true>, dim3(grid), dim3(NT), 0, st, H, W, prm, img, gt, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12,
                                             reinterpret_cast<const double*>(stats), g_loss, dL_dimg);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
@@ -103,7 +104,7 @@ int cg_rotate_channels(int64_t n, const float* in, const float* m3x3, int32_t ld
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   count_launches(1);
   const int64_t nthreads = (n + 3) / 4;
-  rotate_channels_kernel<<<unsigned((nthreads + 255) / 256), 256, 0, st>>>(n, in, m3x3, ld, transpose, out);
+  launch_k(rotate_channels_kernel, dim3(unsigned((nthreads + 255) / 256)), dim3(256), 0, st, n, in, m3x3, ld, transpose, out);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }

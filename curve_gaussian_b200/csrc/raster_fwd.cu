@@ -38,6 +38,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
                const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
                int W, int H, float tanx, float tany, float fx, float fy, int grid_x, int grid_y,
                int antialiasing, int32_t* __restrict__ radii, GeomState g) {
+  pdl_wait();
   __shared__ __align__(16) float s_mean[768];
   __shared__ __align__(16) float s_scale[768];
   __shared__ float s_vm[16], s_pm[16];
@@ -127,6 +128,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
 
 // Single CTA: exclusive scan of the per-block sums, total -> g.total[0].
 __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState g) {
+  pdl_wait();
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
 // their key only has to be deterministic), value = Gaussian index.
 __global__ void __launch_bounds__(256)
 init_depth_keys(int64_t P, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  pdl_wait();
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= P) return;
   keys[i] = g.tiles[i] ? __float_as_uint(g.depth[i]) : 0xffffffffu;
@@ -173,6 +176,7 @@ init_depth_keys(int64_t P, GeomState g, uint32_t* __restrict__ keys, uint32_t* _
 // Block sums of tiles_touched taken in depth order (perm = Gaussian indices sorted by depth).
 __global__ void __launch_bounds__(256)
 perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
+  pdl_wait();
   __shared__ uint32_t s_wsum[8];
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   uint32_t v = (i < P) ? g.tiles[perm[i]] : 0u;
@@ -196,6 +200,7 @@ perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
 __global__ void __launch_bounds__(256)
 emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x, uint32_t* __restrict__ keys,
           uint32_t* __restrict__ vals) {
+  pdl_wait();
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_off[257];
   __shared__ uint32_t s_idx[256];
@@ -242,6 +247,7 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
 __global__ void __launch_bounds__(256)
 rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_t* __restrict__ point_list,
              const float* __restrict__ depth, uint64_t* __restrict__ keys) {
+  pdl_wait();
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
   keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(256)
 gather_records(int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint32_t* __restrict__ sorted_vals,
                GeomState g, const float* __restrict__ colors, const float* __restrict__ all_map,
                uint2* __restrict__ ranges, Rec* __restrict__ rec, uint32_t* __restrict__ point_list) {
+  pdl_wait();
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
   {
@@ -318,6 +325,7 @@ constexpr int BATCH = BLEND_THREADS;
 __global__ void __launch_bounds__(1024)
 order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ maxc,
             uint32_t* __restrict__ tile_order) {
+  pdl_wait();
   __shared__ uint32_t s_cnt[1024];
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_max;
@@ -366,6 +374,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
           const Rec* __restrict__ rec, int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
           uint32_t* __restrict__ tile_maxc) {
+  pdl_wait();
   __shared__ __align__(128) Rec s_rec[2][BATCH];
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ uint32_t s_maxc;
@@ -492,6 +501,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mark_visible_kernel(int64_t P, const float* __restrict__ means3D, const float* __restrict__ vm, uint8_t* __restrict__ present) {
+  pdl_wait();
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= P) return;
   const float3 v = xform43(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2], vm);
@@ -509,12 +519,12 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   const float fy = H / (2.0f * s->tanfovy), fx = W / (2.0f * s->tanfovx);
   const int64_t nblk = (P + 255) / 256;
   { StageTimer t_(ST_PREPROCESS_FWD, st, 1);
-  preprocess_fwd<<<unsigned(nblk), 256, 0, st>>>(P, means3D, opacities, scales, rotations, cov3D_precomp,
+  launch_k(preprocess_fwd, dim3(unsigned(nblk)), dim3(256), 0, st, P, means3D, opacities, scales, rotations, cov3D_precomp,
                                                  s->scale_modifier, s->viewmatrix, s->projmatrix, W, H, s->tanfovx,
                                                  s->tanfovy, fx, fy, gx, gy, s->antialiasing, radii, g); }
   CG_LAUNCH_CHECK(s->debug, st);
   { StageTimer t_(ST_SCAN, st, 1);
-  scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
+  launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g); }
   CG_LAUNCH_CHECK(s->debug, st);
   // R goes to pinned host memory; the host then waits on an EVENT recorded right behind that copy while the
   // stream already carries the next, R-independent stage (depth sort of the Gaussians + offsets in depth
@@ -533,13 +543,13 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   {
     int rc, gcur = 0;
     { StageTimer t_(ST_SORT, st, 1);
-    init_depth_keys<<<unsigned(nblk), 256, 0, st>>>(P, g, g.gs.keys[0], g.gs.vals[0]);
+    launch_k(init_depth_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, g, g.gs.keys[0], g.gs.vals[0]);
     CG_LAUNCH_CHECK(s->debug, st);
     rc = radix_sort_pairs<uint32_t>(g.gs, P, 32, &gcur, s->debug != 0, st); }
     if (rc != CG_OK) return rc;
     { StageTimer t_(ST_SCAN, st, 2);
-    perm_block_sums<<<unsigned(nblk), 256, 0, st>>>(P, g.gs.vals[gcur], g);
-    scan_block_sums<<<1, 1024, 0, st>>>(nblk, g); }
+    launch_k(perm_block_sums, dim3(unsigned(nblk)), dim3(256), 0, st, P, g.gs.vals[gcur], g);
+    launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   CG_CUDA(cudaEventSynchronize(h_event[dev]));
@@ -566,7 +576,7 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     // here: one (tile, Gaussian) pair per overlapped tile
     const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];
     { StageTimer t_(ST_EMIT_KEYS, st, 1);
-    emit_keys<<<unsigned(nblk), 256, 0, st>>>(P, perm, g, gx, bs.is.keys[0], bs.is.vals[0]); }
+    launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, gx, bs.is.keys[0], bs.is.vals[0]); }
     CG_LAUNCH_CHECK(s->debug, st);
     // stable sort by tile only
     int cur = 0;
@@ -576,23 +586,23 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned((R + 255) / 256);
     { StageTimer t_(ST_GATHER, st, 1);
-    gather_records<<<rb, 256, 0, st>>>(R, bs.is.keys[cur], bs.is.vals[cur], g, colors,
+    launch_k(gather_records, dim3(rb), dim3(256), 0, st, R, bs.is.keys[cur], bs.is.vals[cur], g, colors,
                                        s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   const dim3 grid{unsigned(tiles) * BLEND_SUBS, 1u, 1u}, block{unsigned(BLEND_THREADS), 1u, 1u};
   StageTimer t_blend(ST_BLEND_FWD, st, 3);
-  order_tiles<<<1, 1024, 0, st>>>(uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
+  launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
   CG_LAUNCH_CHECK(s->debug, st);
   if (s->render_geo)
-    blend_fwd<true><<<grid, block, 0, st>>>(im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
+    launch_k(blend_fwd<true>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
                                             out_map, im.final_T, im.n_contrib, im.tile_maxc);
   else
-    blend_fwd<false><<<grid, block, 0, st>>>(im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
+    launch_k(blend_fwd<false>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
                                              out_map, im.final_T, im.n_contrib, im.tile_maxc);
   CG_LAUNCH_CHECK(s->debug, st);
   // launch order of the backward CTAs, by the length of list each tile's backward will walk
-  order_tiles<<<1, 1024, 0, st>>>(uint32_t(tiles) * BLEND_SUBS, im.ranges, im.tile_maxc, im.tile_order_bwd);
+  launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, im.tile_maxc, im.tile_order_bwd);
   CG_LAUNCH_CHECK(s->debug, st);
   return CG_OK;
 }
@@ -606,7 +616,7 @@ int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, co
   const size_t tiles = size_t((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
   const int passes = min(4, max(1, (int(tile_key_bits(uint32_t(tiles))) + 7) / 8));
   count_launches(1);
-  rebuild_keys<<<unsigned((R + 255) / 256), 256, 0, st>>>(R, bs.is.keys[passes & 1], bk.point_list, g.depth, dst);
+  launch_k(rebuild_keys, dim3(unsigned((R + 255) / 256)), dim3(256), 0, st, R, bs.is.keys[passes & 1], bk.point_list, g.depth, dst);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }
@@ -614,7 +624,7 @@ int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, co
 int launch_mark_visible(int64_t P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t st) {
   if (P == 0) return CG_OK;
   count_launches(1);
-  mark_visible_kernel<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, means3D, vm, present);
+  launch_k(mark_visible_kernel, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, means3D, vm, present);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }

@@ -86,6 +86,7 @@ __device__ __forceinline__ Axis smooth_pair_grad(Axis x, Axis y) {
 // sums[0] += sum over adjacent pairs of (1 - |cos|)
 __global__ void __launch_bounds__(256)
 curve_smooth_fwd_kernel(int64_t P, int n, const float* __restrict__ rot, double* __restrict__ sums) {
+  pdl_wait();
   __shared__ double s_red[8];
   const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
   double v = 0.0;
@@ -99,12 +100,14 @@ curve_smooth_fwd_kernel(int64_t P, int n, const float* __restrict__ rot, double*
 }
 
 __global__ void curve_smooth_finish_kernel(int64_t npairs, const double* __restrict__ sums, float* __restrict__ loss) {
+  pdl_wait();
   *loss = npairs > 0 ? float(sums[0] / double(npairs)) : 0.f;
 }
 
 __global__ void __launch_bounds__(256)
 curve_smooth_bwd_kernel(int64_t P, int n, const float* __restrict__ rot, const float* __restrict__ g_loss,
                         float scale, float* __restrict__ g_rot) {
+  pdl_wait();
   const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (g >= P) return;
   const int m = int(g % n);
@@ -137,6 +140,7 @@ __device__ __forceinline__ float3 endpoint(const float* __restrict__ cp, int64_t
 __global__ void __launch_bounds__(EP_THREADS)
 endpoint_conn_pairs_kernel(int64_t B, const float* __restrict__ cp, float thr, int64_t chunk,
                            float* __restrict__ part) {
+  pdl_wait();
   __shared__ float4 s_p[EP_THREADS];
   const int64_t N = 2 * B;
   const int64_t i = int64_t(blockIdx.x) * EP_THREADS + threadIdx.x;
@@ -181,6 +185,7 @@ endpoint_conn_pairs_kernel(int64_t B, const float* __restrict__ cp, float thr, i
 __global__ void __launch_bounds__(256)
 endpoint_conn_fold_kernel(int64_t N, int chunks, const float* __restrict__ part, float* __restrict__ v,
                           double* __restrict__ sums) {
+  pdl_wait();
   __shared__ double s_red[8];
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   double s = 0.0, c = 0.0;
@@ -199,6 +204,7 @@ endpoint_conn_fold_kernel(int64_t N, int chunks, const float* __restrict__ part,
 }
 
 __global__ void endpoint_conn_finish_kernel(const double* __restrict__ sums, float* __restrict__ loss) {
+  pdl_wait();
   *loss = sums[1] > 0.0 ? float(sums[0] / sums[1]) : 0.f;
 }
 
@@ -206,6 +212,7 @@ __global__ void endpoint_conn_finish_kernel(const double* __restrict__ sums, flo
 __global__ void __launch_bounds__(256)
 endpoint_conn_bwd_kernel(int64_t B, const float* __restrict__ v, const double* __restrict__ sums,
                          const float* __restrict__ g_loss, float* __restrict__ g_cp) {
+  pdl_wait();
   const int64_t b = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (b >= B) return;
   const float k = sums[1] > 0.0 ? (g_loss ? __ldg(g_loss) : 1.f) * float(2.0 / sums[1]) : 0.f;
@@ -238,10 +245,10 @@ int cg_curve_smooth_fwd(int64_t B, int32_t n, const float* rotation, void* scrat
   CG_CUDA(cudaMemsetAsync(sums, 0, 64, st));
   count_launches(P > 0 ? 2 : 1);
   if (P > 0) {
-    curve_smooth_fwd_kernel<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, n, rotation, sums);
+    launch_k(curve_smooth_fwd_kernel, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, n, rotation, sums);
     CG_LAUNCH_CHECK(0, st);
   }
-  curve_smooth_finish_kernel<<<1, 1, 0, st>>>(B * (n - 1), sums, loss_out);
+  launch_k(curve_smooth_finish_kernel, dim3(1), dim3(1), 0, st, B * (n - 1), sums, loss_out);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }
@@ -255,7 +262,7 @@ int cg_curve_smooth_bwd(int64_t B, int32_t n, const float* rotation, const float
          "rotation/g_rotation must be 16-byte aligned");
   const int64_t P = B * n, npairs = B * (n - 1);
   count_launches(1);
-  curve_smooth_bwd_kernel<<<unsigned((P + 255) / 256), 256, 0, st>>>(P, n, rotation, g_loss,
+  launch_k(curve_smooth_bwd_kernel, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, n, rotation, g_loss,
                                                                     npairs > 0 ? 1.0f / float(npairs) : 0.f, g_rotation);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
@@ -291,13 +298,13 @@ int cg_endpoint_conn_fwd(int64_t B, const float* curve_points, float dis_thr, vo
     float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 64);
     dim3 grid(unsigned((N + EP_THREADS - 1) / EP_THREADS), unsigned((N + chunk - 1) / chunk));
     count_launches(2);
-    endpoint_conn_pairs_kernel<<<grid, EP_THREADS, 0, st>>>(B, curve_points, dis_thr, chunk, part);
+    launch_k(endpoint_conn_pairs_kernel, dim3(grid), dim3(EP_THREADS), 0, st, B, curve_points, dis_thr, chunk, part);
     CG_LAUNCH_CHECK(0, st);
-    endpoint_conn_fold_kernel<<<unsigned((N + 255) / 256), 256, 0, st>>>(N, int(grid.y), part, v, sums);
+    launch_k(endpoint_conn_fold_kernel, dim3(unsigned((N + 255) / 256)), dim3(256), 0, st, N, int(grid.y), part, v, sums);
     CG_LAUNCH_CHECK(0, st);
   }
   count_launches(1);
-  endpoint_conn_finish_kernel<<<1, 1, 0, st>>>(sums, loss_out);
+  launch_k(endpoint_conn_finish_kernel, dim3(1), dim3(1), 0, st, sums, loss_out);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }
@@ -308,7 +315,7 @@ int cg_endpoint_conn_bwd(int64_t B, const float* v, const void* scratch, const f
   if (B == 0) return CG_OK;
   CG_ARG(B > 0 && v && scratch && g_curve_points, "endpoint_conn_bwd arguments");
   count_launches(1);
-  endpoint_conn_bwd_kernel<<<unsigned((B + 255) / 256), 256, 0, st>>>(B, v, reinterpret_cast<const double*>(scratch),
+  launch_k(endpoint_conn_bwd_kernel, dim3(unsigned((B + 255) / 256)), dim3(256), 0, st, B, v, reinterpret_cast<const double*>(scratch),
                                                                      g_loss, g_curve_points);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;

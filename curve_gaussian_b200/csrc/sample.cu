@@ -151,6 +151,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 __global__ void __launch_bounds__(256)
 sample_reduce_fwd(int64_t B, int n, const float* __restrict__ cp, const uint8_t* __restrict__ is_bezier,
                   const float* __restrict__ tt, double* __restrict__ sums) {
+  pdl_wait();
   __shared__ double sm[8];
   const int64_t P = B * n;
   double s1 = 0.0, s2 = 0.0;
@@ -172,6 +173,7 @@ sample_fwd_main(int64_t B, int n, const float* __restrict__ cp, const float* __r
                 const uint8_t* __restrict__ is_bezier, const float* __restrict__ tt, float half_step,
                 const double* __restrict__ sums, float* __restrict__ xyz, float* __restrict__ rot,
                 float* __restrict__ scaling, float* __restrict__ norms) {
+  pdl_wait();
   const int64_t P = B * n;
   const int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const float N1 = float(sqrt(sums[0]));
@@ -239,6 +241,7 @@ sample_bwd_point(int64_t B, int n, const float* __restrict__ cp, const uint8_t* 
                  const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
                  const float* __restrict__ dL_dxyz, const float* __restrict__ dL_drot,
                  const float* __restrict__ dL_dscaling, float* __restrict__ pt, double* __restrict__ sums) {
+  pdl_wait();
   __shared__ double s_red[8];
   const int64_t P = B * n;
   const int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -307,6 +310,7 @@ sample_bwd_curve(int64_t B, int n, const float* __restrict__ width, const uint8_
                  const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
                  const double* __restrict__ sums, const float* __restrict__ pt, const float* __restrict__ dL_dscaling,
                  float* __restrict__ dL_dcp, float* __restrict__ dL_dwidth) {
+  pdl_wait();
   const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -378,9 +382,9 @@ int cg_sample_fwd(int64_t B, int32_t n, const float* curve_points, const float* 
   CG_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(double), st));
   const int rb = int((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
   StageTimer t_(ST_SAMPLE_FWD, st, 2);
-  sample_reduce_fwd<<<rb, 256, 0, st>>>(B, n, curve_points, is_bezier, t, sums);
+  launch_k(sample_reduce_fwd, dim3(rb), dim3(256), 0, st, B, n, curve_points, is_bezier, t, sums);
   CG_LAUNCH_CHECK(0, st);
-  sample_fwd_main<<<unsigned((P + 255) / 256), 256, 0, st>>>(B, n, curve_points, width, is_bezier, t, half_step, sums,
+  launch_k(sample_fwd_main, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, B, n, curve_points, width, is_bezier, t, half_step, sums,
                                                              xyz, rotation, scaling, norms);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
@@ -400,10 +404,10 @@ int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* 
   CG_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(double), st));
   float* pt = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 128);
   StageTimer t_(ST_SAMPLE_BWD, st, 2);
-  sample_bwd_point<<<unsigned((P + 255) / 256), 256, 0, st>>>(B, n, curve_points, is_bezier, t, half_step, norms, dL_dxyz,
+  launch_k(sample_bwd_point, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, B, n, curve_points, is_bezier, t, half_step, norms, dL_dxyz,
                                                              dL_drotation, dL_dscaling, pt, sums);
   CG_LAUNCH_CHECK(0, st);
-  sample_bwd_curve<<<unsigned((B * 32 + 255) / 256), 256, 0, st>>>(B, n, width, is_bezier, t, half_step, norms, sums, pt,
+  launch_k(sample_bwd_curve, dim3(unsigned((B * 32 + 255) / 256)), dim3(256), 0, st, B, n, width, is_bezier, t, half_step, norms, sums, pt,
                                                                   dL_dscaling, dL_dcurve_points, dL_dwidth);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;

@@ -33,6 +33,7 @@ constexpr uint32_t FLAG_INC = 2u;   // inclusive prefix published
 template <typename K>
 __global__ void __launch_bounds__(256)
 sort_histogram(const K* __restrict__ keys, int64_t R, int passes, int bpp, uint32_t* __restrict__ hist) {
+  pdl_wait();
   __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
   for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -50,6 +51,7 @@ sort_histogram(const K* __restrict__ keys, int64_t R, int passes, int bpp, uint3
 
 // One CTA per pass: in-place exclusive scan of that pass's 256 bins.
 __global__ void __launch_bounds__(256) sort_scan_bins(uint32_t* __restrict__ hist) {
+  pdl_wait();
   __shared__ uint32_t wsum[8];
   uint32_t* h = hist + blockIdx.x * 256;
   uint32_t v = h[threadIdx.x];
@@ -82,6 +84,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
                    K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                    int64_t R, int shift, uint32_t dmask, const uint32_t* __restrict__ digit_base,
                    uint32_t* __restrict__ ticket, uint32_t* __restrict__ status) {
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SortSmem<K>& s = *reinterpret_cast<SortSmem<K>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -272,15 +275,14 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
 
   int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
   count_launches(2 + passes);
-  sort_histogram<K><<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, bpp, b.hist);
+  launch_k(sort_histogram<K>, dim3(hist_blocks), dim3(256), 0, stream, b.keys[0], R, passes, bpp, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
-  sort_scan_bins<<<passes, 256, 0, stream>>>(b.hist);
+  launch_k(sort_scan_bins, dim3(passes), dim3(256), 0, stream, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
 
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
-    sort_onesweep_pass<K><<<unsigned(ntiles), SORT_THREADS, sizeof(SortSmem<K>), stream>>>(
-        b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, bpp * p, dmask,
+    launch_k(sort_onesweep_pass<K>, dim3(unsigned(ntiles)), dim3(SORT_THREADS), sizeof(SortSmem<K>), stream, b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, bpp * p, dmask,
         b.hist + p * 256, b.ticket + p, b.status + size_t(p) * ntiles * 256);
     CG_LAUNCH_CHECK(debug, stream);
     cur ^= 1;

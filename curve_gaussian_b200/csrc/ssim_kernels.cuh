@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(NT, 3)
 ssim_fwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, const float* __restrict__ img2,
                 float* __restrict__ ssim_map, float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
                 float* __restrict__ dm_dsigma12, double* __restrict__ stats, float* __restrict__ loss_out) {
+  pdl_wait();
   __shared__ float s1[IN][IN + 1];
   __shared__ float s2[IN][IN + 1];
   __shared__ float hq[5][IN][TS + 1];   // +1: the RUN-strided stores of the horizontal pass stay conflict-free
@@ -189,6 +190,7 @@ ssim_bwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, co
                 const float* __restrict__ dL_dmap, const float* __restrict__ dm_dmu1,
                 const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
                 const double* __restrict__ stats, const float* __restrict__ g_loss, float* __restrict__ dL_dimg1) {
+  pdl_wait();
   __shared__ float sp[3][IN][IN + 1];
   __shared__ float hq[3][IN][TS + 1];
   const size_t plane = size_t(blockIdx.z) * H * W;
