@@ -228,15 +228,17 @@ def run_ours(a):
         else:
             gt = gts_dev[i % len(cams)]
         model.prepare_scaling_rot()
-        image = render(cam, model, pipe, bg)["render"]
+        pkg = render(cam, model, pipe, bg)
         R_seen.append(rz.rasterize_forward_raw.last_R)
         if a.unfused_loss:
+            image = pkg["render"]
             Ll1 = edge_aware_loss(image, gt)
             ssim_value = fused_ssim(image.unsqueeze(0), gt.unsqueeze(0))
             loss = 10.0 * (0.9 * Ll1 + 0.1 * (1.0 - ssim_value))
         else:
             # the same scalar (train.py:101-107) as one fused forward + one fused backward kernel
-            loss = edge_ssim_loss(image, gt, threshold=0.1, lambda_mse=10.0, lambda_dssim=0.1)
+            # (render()'s clamp(0,1) is fused in too: the op takes the raw render)
+            loss = edge_ssim_loss(pkg["render_raw"], gt, threshold=0.1, lambda_mse=10.0, lambda_dssim=0.1, clamp=True)
         loss.backward()
         fg.all_reduce()
         if host_io:

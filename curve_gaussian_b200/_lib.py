@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcurvegs.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class RasterSettings(C.Structure):
@@ -67,8 +67,8 @@ SIGNATURES = {
     "cg_ssim_fwd": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_ssim_bwd": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_edge_ssim_loss_stats_bytes": (_sz, []),
-    "cg_edge_ssim_loss_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cg_edge_ssim_loss_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_edge_ssim_loss_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_edge_ssim_loss_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_rotate_channels": (C.c_int, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "cg_curve_smooth_scratch_bytes": (_sz, []),
     "cg_curve_smooth_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp]),

@@ -96,7 +96,7 @@ using namespace cg;
 
 extern "C" {
 
-int cg_abi_version(void) { return 3; }
+int cg_abi_version(void) { return 4; }
 uint64_t cg_launch_count(void) { return g_launches.load(); }
 void cg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 void cg_profile_reset(void) {

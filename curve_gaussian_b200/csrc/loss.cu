@@ -63,8 +63,8 @@ extern "C" {
 size_t cg_edge_ssim_loss_stats_bytes(void) { return 8 * sizeof(double); }
 
 int cg_edge_ssim_loss_fwd(int32_t H, int32_t W, const float* img, const float* gt, float threshold, float lambda_mse,
-                          float lambda_dssim, float C1, float C2, void* stats, float* loss_out, float* dm_dmu1,
-                          float* dm_dsigma1_sq, float* dm_dsigma12, void* stream) {
+                          float lambda_dssim, float C1, float C2, int32_t clamp01, void* stats, float* loss_out,
+                          float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* stream) {
   CG_ARG(H > 0 && W > 0, "image shape");
   CG_ARG(img && gt && stats && loss_out, "edge_ssim_loss_fwd pointers");
   CG_ARG((dm_dmu1 && dm_dsigma1_sq && dm_dsigma12) || (!dm_dmu1 && !dm_dsigma1_sq && !dm_dsigma12),
@@ -73,7 +73,7 @@ int cg_edge_ssim_loss_fwd(int32_t H, int32_t W, const float* img, const float* g
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CG_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS);
-  LossParams prm{threshold, lambda_mse, lambda_dssim, C1, C2};
+  LossParams prm{threshold, lambda_mse, lambda_dssim, C1, C2, clamp01 ? 1 : 0};
   StageTimer t_(ST_LOSS_FWD, st, 1);
   launch_k(ssim_fwd_kernel<true>, dim3(grid), dim3(NT), 0, st, H, W, prm, img, gt, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12,
                                             reinterpret_cast<double*>(stats), loss_out);
@@ -82,13 +82,13 @@ int cg_edge_ssim_loss_fwd(int32_t H, int32_t W, const float* img, const float* g
 }
 
 int cg_edge_ssim_loss_bwd(int32_t H, int32_t W, const float* img, const float* gt, float threshold, float lambda_mse,
-                          float lambda_dssim, const void* stats, const float* g_loss, const float* dm_dmu1,
+                          float lambda_dssim, int32_t clamp01, const void* stats, const float* g_loss, const float* dm_dmu1,
                           const float* dm_dsigma1_sq, const float* dm_dsigma12, float* dL_dimg, void* stream) {
   CG_ARG(H > 0 && W > 0, "image shape");
   CG_ARG(img && gt && stats && dm_dmu1 && dm_dsigma1_sq && dm_dsigma12 && dL_dimg, "edge_ssim_loss_bwd pointers");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS);
-  LossParams prm{threshold, lambda_mse, lambda_dssim, 0.f, 0.f};
+  LossParams prm{threshold, lambda_mse, lambda_dssim, 0.f, 0.f, clamp01 ? 1 : 0};
   StageTimer t_(ST_LOSS_BWD, st, 1);
   launch_k(ssim_bwd_kernel<true>, dim3(grid), dim3(NT), 0, st, H, W, prm, img, gt, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12,
                                             reinterpret_cast<const double*>(stats), g_loss, dL_dimg);

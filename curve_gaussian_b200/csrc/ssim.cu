@@ -17,7 +17,7 @@ int cg_ssim_fwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
   CG_ARG(int64_t(B) * CH <= 65535, "B*CH");
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, B * CH);
   StageTimer t_(ST_SSIM_FWD, reinterpret_cast<cudaStream_t>(stream), 1);
-  LossParams prm{0.f, 0.f, 0.f, C1, C2};
+  LossParams prm{0.f, 0.f, 0.f, C1, C2, 0};
   launch_k(ssim_fwd_kernel<false>, dim3(grid), dim3(NT), 0, reinterpret_cast<cudaStream_t>(stream), H, W, prm, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, nullptr, nullptr);
   CG_LAUNCH_CHECK(0, reinterpret_cast<cudaStream_t>(stream));
   return CG_OK;
@@ -33,7 +33,7 @@ int cg_ssim_bwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
   CG_ARG(int64_t(B) * CH <= 65535, "B*CH");
   dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, B * CH);
   StageTimer t_(ST_SSIM_BWD, reinterpret_cast<cudaStream_t>(stream), 1);
-  LossParams prm{0.f, 0.f, 0.f, 0.f, 0.f};
+  LossParams prm{0.f, 0.f, 0.f, 0.f, 0.f, 0};
   launch_k(ssim_bwd_kernel<false>, dim3(grid), dim3(NT), 0, reinterpret_cast<cudaStream_t>(stream), H, W, prm, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, nullptr, nullptr, dL_dimg1);
   CG_LAUNCH_CHECK(0, reinterpret_cast<cudaStream_t>(stream));
   return CG_OK;

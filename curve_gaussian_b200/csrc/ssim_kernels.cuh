@@ -35,7 +35,11 @@ __device__ __forceinline__ float load_px(const float* __restrict__ img, int y, i
 
 struct LossParams {
   float threshold, lambda_mse, lambda_dssim, C1, C2;
+  int clamp01;   // LOSS variants: img1 is the raw render; clamp it to [0,1] on load (render()'s clamp, fused)
 };
+
+// torch.clamp(x, 0, 1) including its NaN behaviour (NaN stays NaN)
+__device__ __forceinline__ float clamp01f(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
 __device__ __forceinline__ double block_sum_d(double v, double* s_red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -67,7 +71,9 @@ ssim_fwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, co
   const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
   for (int i = threadIdx.x; i < IN * IN; i += NT) {
     const int ly = i / IN, lx = i - ly * IN;
-    s1[ly][lx] = load_px(a, y0 + ly - HALO, x0 + lx - HALO, H, W);
+    float va = load_px(a, y0 + ly - HALO, x0 + lx - HALO, H, W);
+    if (LOSS && prm.clamp01) va = clamp01f(va);
+    s1[ly][lx] = va;
     s2[ly][lx] = load_px(b, y0 + ly - HALO, x0 + lx - HALO, H, W);
   }
   __syncthreads();
@@ -252,14 +258,17 @@ ssim_bwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, co
     const int x = x0 + lx, y = y0 + ly0 + r;
     if (x < W && y < H) {
       const size_t o = plane + size_t(y) * W + x;
-      const float p1 = __ldg(img1 + o), p2 = __ldg(img2 + o);
+      const float p1raw = __ldg(img1 + o), p2 = __ldg(img2 + o);
+      const float p1 = (LOSS && prm.clamp01) ? clamp01f(p1raw) : p1raw;
       float d = 0.f;
       d += v0;
       d += p1 * 2.0f * v1;
       d += p2 * v2;
       if (LOSS) {
         const float w = (p2 > prm.threshold) ? w_pos : w_neg;
-        dL_dimg1[o] = k_mse * w * (p1 - p2) + k_ssim * d;
+        const float gval = k_mse * w * (p1 - p2) + k_ssim * d;
+        // clamp's adjoint: the gradient passes where 0 <= x <= 1 (and not for NaN), like torch.clamp
+        dL_dimg1[o] = (!prm.clamp01 || (p1raw >= 0.f && p1raw <= 1.f)) ? gval : 0.f;
       } else {
         dL_dimg1[o] = d;
       }

@@ -29,7 +29,7 @@ def edge_aware_loss(image, gt_image, threshold=0.1):
 
 class _EdgeSSIMLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, image, gt, threshold, lambda_mse, lambda_dssim):
+    def forward(ctx, image, gt, threshold, lambda_mse, lambda_dssim, clamp):
         lib = _lib.load()
         if not image.is_cuda:
             raise _lib.CurveGSError("edge_ssim_loss needs CUDA tensors; there is no CPU path")
@@ -47,33 +47,34 @@ class _EdgeSSIMLoss(torch.autograd.Function):
         d3 = torch.empty_like(a) if train else None
         with _lib.on_device(dev):
             _lib.check(lib.cg_edge_ssim_loss_fwd(H, W, a.data_ptr(), b.data_ptr(), float(threshold), float(lambda_mse),
-                                                 float(lambda_dssim), 0.01 ** 2, 0.03 ** 2, stats.data_ptr(),
+                                                 float(lambda_dssim), 0.01 ** 2, 0.03 ** 2, int(bool(clamp)), stats.data_ptr(),
                                                  loss.data_ptr(), _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(d3),
                                                  _lib.stream(dev)), "cg_edge_ssim_loss_fwd")
         if train:
             ctx.save_for_backward(a, b, stats, d1, d2, d3)
-        ctx.meta = (H, W, float(threshold), float(lambda_mse), float(lambda_dssim), tuple(image.shape))
+        ctx.meta = (H, W, float(threshold), float(lambda_mse), float(lambda_dssim), int(bool(clamp)), tuple(image.shape))
         return loss
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         a, b, stats, d1, d2, d3 = ctx.saved_tensors
-        H, W, thr, lm, ld, shape = ctx.meta
+        H, W, thr, lm, ld, clamp, shape = ctx.meta
         out = torch.empty_like(a)
         g = g.float().contiguous()
         with _lib.on_device(a.device):
-            _lib.check(lib.cg_edge_ssim_loss_bwd(H, W, a.data_ptr(), b.data_ptr(), thr, lm, ld, stats.data_ptr(),
+            _lib.check(lib.cg_edge_ssim_loss_bwd(H, W, a.data_ptr(), b.data_ptr(), thr, lm, ld, clamp, stats.data_ptr(),
                                                  g.data_ptr(), d1.data_ptr(), d2.data_ptr(), d3.data_ptr(),
                                                  out.data_ptr(), _lib.stream(a.device)),
                        "cg_edge_ssim_loss_bwd")
-        return out.view(shape), None, None, None, None
+        return out.view(shape), None, None, None, None, None
 
 
-def edge_ssim_loss(image, gt_image, threshold=0.1, lambda_mse=10.0, lambda_dssim=0.1):
+def edge_ssim_loss(image, gt_image, threshold=0.1, lambda_mse=10.0, lambda_dssim=0.1, clamp=False):
     """Device scalar lambda_mse*((1-lambda_dssim)*edge_aware_loss + lambda_dssim*(1-ssim)); defaults are the
-    reference's OptimizationParams (arguments/__init__.py:94-110)."""
-    return _EdgeSSIMLoss.apply(image, gt_image, threshold, lambda_mse, lambda_dssim)
+    reference's OptimizationParams (arguments/__init__.py:94-110). With clamp=True `image` is the raw render
+    (`render(...)["render_raw"]`) and render()'s clamp(0,1) is applied inside the kernels, forward and adjoint."""
+    return _EdgeSSIMLoss.apply(image, gt_image, threshold, lambda_mse, lambda_dssim, clamp)
 
 
 class _RotateChannels(torch.autograd.Function):

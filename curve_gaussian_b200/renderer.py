@@ -63,6 +63,19 @@ class RenderPackage(dict):
         return super().items()
 
 
+_ONES = {}
+
+
+def _ones(P: int, dev) -> torch.Tensor:
+    """(P,1) ones (the single colour channel, gaussian_renderer/__init__.py:97), cached per size and device."""
+    key = (int(P), str(dev))
+    t = _ONES.get(key)
+    if t is None:
+        _ONES.clear()
+        t = _ONES[key] = torch.ones(P, 1, device=dev)
+    return t
+
+
 def _can_fuse(pc) -> bool:
     """The fused activation needs the curve model's raw tensors (the reference class has them too)."""
     need = ("_xyz", "_rotation", "_scaling", "_opacity", "_mask", "n_gaussians")
@@ -75,12 +88,10 @@ def _can_fuse(pc) -> bool:
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, separate_sh=False,
            override_color=None, use_trained_exp=False, use_mask=False, mask_thr=0.01):
     """Render the scene. Background tensor (bg_color) must be on GPU."""
+    # the reference makes this a non-leaf (`zeros_like(...) + 0`, then retain_grad()); a fresh leaf gives
+    # callers the same `.grad` with one fill kernel instead of two
     screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True,
-                                          device=pc.get_xyz.device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+                                          device=pc.get_xyz.device)
 
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
     tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
@@ -105,7 +116,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     means3D = pc.get_xyz
     means2D = screenspace_points
     dev = means3D.device
-    colors_precomp = torch.ones(means3D.shape[0], 1, device=dev)
+    colors_precomp = _ones(means3D.shape[0], dev)
     if _can_fuse(pc):
         # one fused kernel for normalize / sigmoid / mask straight-through / main axis / all_map
         rotations, opacity, scales, input_all_map = curve_activate(
@@ -133,17 +144,18 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         rendered_image = torch.matmul(rendered_image.permute(1, 2, 0), exposure[:3, :3]).permute(2, 0, 1) \
             + exposure[:3, 3, None, None]
 
-    rendered_image = rendered_image.clamp(0, 1)
+    raw_image = rendered_image
     rendered_alpha = out_all_map[3:4, ]
     wvt = viewpoint_camera.world_view_transform
 
     return RenderPackage({
-        "render": rendered_image,
+        "render_raw": raw_image,     # extra key: the render before clamp(0,1), for losses that fuse the clamp
         "viewspace_points": screenspace_points,
         "radii": radii,
         "depth": depth_image,
         "rend_alpha": rendered_alpha,
     }, {
+        "render": lambda: raw_image.clamp(0, 1),
         "visibility_filter": lambda: (radii > 0).nonzero(),
         # (dir.permute(1,2,0) @ wvt[:3,:3].T).permute(2,0,1) as one per-pixel kernel
         "rend_dir": lambda: rotate_channels(out_all_map[0:3], wvt[:3, :3]),

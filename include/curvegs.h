@@ -219,14 +219,17 @@ int cg_ssim_bwd(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
  * (class-balanced weighted MSE) and fused_ssim (fused-ssim/ssim.cu:187-366) in ONE
  * forward and ONE backward kernel. loss_out is a DEVICE scalar (no host sync). stats
  * is cg_edge_ssim_loss_stats_bytes() of device memory kept for the backward together
- * with the three partial maps. g_loss is the DEVICE upstream scalar (NULL = 1). */
+ * with the three partial maps. g_loss is the DEVICE upstream scalar (NULL = 1).
+ * clamp01 != 0: img is the RAW render and the clamp(0,1) render() applies
+ * (gaussian_renderer/__init__.py:139) is fused in: values are clamped on load and the
+ * gradient is zeroed outside [0,1], exactly like torch.clamp's adjoint. */
 size_t cg_edge_ssim_loss_stats_bytes(void);
 int cg_edge_ssim_loss_fwd(int32_t H, int32_t W, const float* img, const float* gt,
                           float threshold, float lambda_mse, float lambda_dssim, float C1, float C2,
-                          void* stats, float* loss_out,
+                          int32_t clamp01, void* stats, float* loss_out,
                           float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* stream);
 int cg_edge_ssim_loss_bwd(int32_t H, int32_t W, const float* img, const float* gt,
-                          float threshold, float lambda_mse, float lambda_dssim,
+                          float threshold, float lambda_mse, float lambda_dssim, int32_t clamp01,
                           const void* stats, const float* g_loss,
                           const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
                           float* dL_dimg, void* stream);

@@ -81,3 +81,22 @@ def test_rotate_channels_matches_matmul(cuda_dev, shape):
     (out * gw).sum().backward()
     (ref * gw).sum().backward()
     assert rel(planes.grad, p2.grad) <= 1e-6
+
+
+def test_fused_clamp_equals_torch_clamp_then_loss(cuda_dev):
+    """clamp=True on the raw render == render()'s torch clamp(0,1) followed by the loss, value and gradient
+    (zero outside [0,1], passed on the closed interval's ends, like torch.clamp's adjoint)."""
+    g = torch.Generator().manual_seed(11)
+    raw = torch.rand(1, 90, 130, generator=g) * 1.6 - 0.3          # a good share below 0 and above 1
+    raw[0, 0, :4] = torch.tensor([0.0, 1.0, -0.0, 1.0000001])
+    gt = (torch.rand(1, 90, 130, generator=g) < 0.1).float()
+    a = raw.to(cuda_dev).requires_grad_(True)
+    loss = edge_ssim_loss(a, gt.to(cuda_dev), clamp=True)
+    loss.backward()
+    b = raw.to(cuda_dev).requires_grad_(True)
+    ref = edge_ssim_loss(b.clamp(0, 1), gt.to(cuda_dev))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert rel(a.grad, b.grad) <= 1e-6
+    outside = (raw < 0) | (raw > 1)
+    assert float(a.grad.cpu()[outside].abs().max()) == 0.0
