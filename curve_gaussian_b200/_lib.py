@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcurvegs.so")
+# CURVEGS_LIB selects another build of the same library (A/B timing of kernel variants, see build.build_variant)
+LIB_PATH = os.environ.get("CURVEGS_LIB") or os.path.join(_HERE, "libcurvegs.so")
 
 ABI_VERSION = 4
 
