@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_use_pdl = 1;
+
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_profile{0};
 struct ProfRec { int stage; cudaEvent_t e0, e1; };
@@ -71,7 +73,7 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
                     int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st);
 int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
                      void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
-                     float* out_map, cudaStream_t st);
+                     float* out_map, uint32_t* nr_out, cudaStream_t st);
 int launch_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* means3D, const float* opacities,
                const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
                const void* geom, const void* img, const void* bin_keep, const float* dL_dcolor,
@@ -96,7 +98,8 @@ using namespace cg;
 
 extern "C" {
 
-int cg_abi_version(void) { return 4; }
+int cg_abi_version(void) { return 5; }
+void cg_set_pdl(int on) { g_use_pdl = on ? 1 : 0; }
 uint64_t cg_launch_count(void) { return g_launches.load(); }
 void cg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 void cg_profile_reset(void) {
@@ -174,7 +177,37 @@ int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const
     CG_ARG(!all_map || (reinterpret_cast<uintptr_t>(all_map) & 15u) == 0, "all_map must be 16-byte aligned");
   }
   return launch_fwd_blend(s, P, R, colors, all_map, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
-                          out_all_map, reinterpret_cast<cudaStream_t>(stream));
+                          out_all_map, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cg_raster_fwd_capacity(const cg_raster_settings* s, int64_t P, int64_t R_cap, const float* means3D,
+                           const float* opacities, const float* scales, const float* rotations,
+                           const float* cov3D_precomp, const float* colors, const float* all_map, int32_t* radii,
+                           void* geom, size_t geom_bytes, void* img, void* bin_keep, void* bin_scratch,
+                           float* out_color, float* out_invdepth, float* out_all_map, uint32_t* num_rendered_dev,
+                           void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  CG_ARG(P > 0 && P < (int64_t(1) << 31), "P");
+  CG_ARG(R_cap > 0 && R_cap < (int64_t(1) << 30), "R_cap");
+  CG_ARG(means3D && opacities && radii && geom && img && colors, "means3D/opacities/radii/geom/img/colors");
+  CG_ARG((scales && rotations && !cov3D_precomp) || (!scales && !rotations && cov3D_precomp),
+         "exactly one of scale/rotation pair or precomputed 3D covariance");
+  CG_ARG(bin_keep && bin_scratch && out_color && out_invdepth && num_rendered_dev,
+         "bin_keep/bin_scratch/out_color/out_invdepth/num_rendered_dev");
+  CG_ARG(!s->render_geo || (out_all_map && all_map), "all_map/out_all_map required with render_geo");
+  if (geom_bytes < cg_raster_geom_bytes(P)) {
+    set_error("geom buffer too small: %zu < %zu", geom_bytes, cg_raster_geom_bytes(P));
+    return CG_ERR_CAPACITY;
+  }
+  CG_ARG(((reinterpret_cast<uintptr_t>(geom) | reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(bin_keep) |
+           reinterpret_cast<uintptr_t>(bin_scratch)) & 127u) == 0, "state buffers must be 128-byte aligned");
+  CG_ARG(!all_map || (reinterpret_cast<uintptr_t>(all_map) & 15u) == 0, "all_map must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  rc = launch_fwd_geom(s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, geom, nullptr, st);
+  if (rc) return rc;
+  return launch_fwd_blend(s, P, R_cap, colors, all_map, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
+                          out_all_map, num_rendered_dev, st);
 }
 
 int cg_raster_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* means3D, const float* opacities,

@@ -49,6 +49,8 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+extern int g_use_pdl;   // cg_set_pdl(); 1 by default
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                             Args&&... args) {
@@ -61,7 +63,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif
@@ -281,8 +283,11 @@ inline uint32_t tile_key_bits(uint32_t n) {
 
 // Stable LSD radix sort of b.keys[0]/b.vals[0] on bits [0,end_bit); *out_buf tells which of the
 // two ping-pong buffers holds the result. Instantiated for uint32_t and uint64_t keys (sort.cu).
+// With d_n != NULL the number of pairs is min(n, *d_n), read on the device: n is then only the capacity the grids
+// and buffers are sized for (sync-free binning, cg_raster_fwd_capacity).
 template <typename K>
-int radix_sort_pairs(const SortBufs<K>& b, int64_t n, int end_bit, int* out_buf, bool debug, cudaStream_t stream);
+int radix_sort_pairs(const SortBufs<K>& b, int64_t n, int end_bit, int* out_buf, bool debug, cudaStream_t stream,
+                     const uint32_t* d_n = nullptr);
 // Which ping-pong buffer radix_sort_pairs leaves the result in (number of digit passes is ceil(end_bit / 8)).
 inline int radix_sort_result_buf(int end_bit) { int p = (end_bit + 7) / 8; return (p < 1 ? 1 : p) & 1; }
 

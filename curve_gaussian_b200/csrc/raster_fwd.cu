@@ -199,8 +199,15 @@ perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
 // work is balanced no matter how uneven the rects are.
 __global__ void __launch_bounds__(256)
 emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x, uint32_t* __restrict__ keys,
-          uint32_t* __restrict__ vals) {
+          uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ nr_out) {
   pdl_wait();
+  // capacity mode: report {R, R > capacity} to the caller's device counter; slots >= cap are dropped below
+  // (the farthest instances, since emission is in depth order) and every later stage works on min(R, cap)
+  if (nr_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t R = g.total[0];
+    nr_out[0] = R;
+    nr_out[1] = R > cap ? 1u : 0u;
+  }
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_off[257];
   __shared__ uint32_t s_idx[256];
@@ -238,8 +245,10 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
     const uint32_t mnx = rc.x & 0xffffu, mny = rc.x >> 16, mxx = rc.y & 0xffffu;
     const uint32_t wdt = mxx - mnx;
     const uint32_t ry = local / wdt, rx = local - ry * wdt;
-    keys[base + o] = (mny + ry) * uint32_t(grid_x) + (mnx + rx);
-    vals[base + o] = s_idx[lo];
+    if (base + o < cap) {
+      keys[base + o] = (mny + ry) * uint32_t(grid_x) + (mnx + rx);
+      vals[base + o] = s_idx[lo];
+    }
   }
 }
 
@@ -255,10 +264,12 @@ rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_
 
 // Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry.
 __global__ void __launch_bounds__(256)
-gather_records(int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint32_t* __restrict__ sorted_vals,
-               GeomState g, const float* __restrict__ colors, const float* __restrict__ all_map,
-               uint2* __restrict__ ranges, Rec* __restrict__ rec, uint32_t* __restrict__ point_list) {
+gather_records(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __restrict__ sorted_tiles,
+               const uint32_t* __restrict__ sorted_vals, GeomState g, const float* __restrict__ colors,
+               const float* __restrict__ all_map, uint2* __restrict__ ranges, Rec* __restrict__ rec,
+               uint32_t* __restrict__ point_list) {
   pdl_wait();
+  if (d_n) R = min(R, int64_t(*d_n));   // capacity mode: the count lives on the device
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= R) return;
   {
@@ -529,17 +540,22 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   // R goes to pinned host memory; the host then waits on an EVENT recorded right behind that copy while the
   // stream already carries the next, R-independent stage (depth sort of the Gaussians + offsets in depth
   // order), so the wake-up latency of the host is hidden behind ~0.1 ms of useful GPU work.
+  // (num_rendered == NULL: capacity mode, R stays on the device and nothing here touches the host)
   int dev = 0;
-  CG_CUDA(cudaGetDevice(&dev));
   static thread_local uint32_t* h_total[64] = {nullptr};
   static thread_local cudaEvent_t h_event[64] = {nullptr};
-  CG_ARG(dev >= 0 && dev < 64, "device ordinal");
-  if (!h_total[dev]) {
+  if (num_rendered) {
+    CG_CUDA(cudaGetDevice(&dev));
+    CG_ARG(dev >= 0 && dev < 64, "device ordinal");
+  }
+  if (num_rendered && !h_total[dev]) {
     CG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_total[dev]), 64, cudaHostAllocDefault));
     CG_CUDA(cudaEventCreateWithFlags(&h_event[dev], cudaEventDisableTiming));
   }
-  CG_CUDA(cudaMemcpyAsync(h_total[dev], g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  CG_CUDA(cudaEventRecord(h_event[dev], st));
+  if (num_rendered) {
+    CG_CUDA(cudaMemcpyAsync(h_total[dev], g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(cudaEventRecord(h_event[dev], st));
+  }
   {
     int rc, gcur = 0;
     { StageTimer t_(ST_SORT, st, 1);
@@ -552,14 +568,20 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
     launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
-  CG_CUDA(cudaEventSynchronize(h_event[dev]));
-  *num_rendered = int64_t(*h_total[dev]);
+  if (num_rendered) {
+    CG_CUDA(cudaEventSynchronize(h_event[dev]));
+    *num_rendered = int64_t(*h_total[dev]);
+  }
   return CG_OK;
 }
 
+// nr_out == NULL: R is the exact instance count (known on the host). nr_out != NULL (capacity mode): R is the
+// capacity of bin_keep / bin_scratch, the true count is read on the device (g.total) by every R-sized kernel and
+// {count, overflow} is written to nr_out.
 int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
                      void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
-                     float* out_map, cudaStream_t st) {
+                     float* out_map, uint32_t* nr_out, cudaStream_t st) {
+  const uint32_t* d_n = nr_out ? GeomState::carve(geom, P, nullptr).total : nullptr;
   GeomState g = GeomState::carve(geom, P, nullptr);
   const int W = s->image_width, H = s->image_height;
   ImgState im = ImgState::carve(img, W, H, nullptr);
@@ -576,17 +598,18 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     // here: one (tile, Gaussian) pair per overlapped tile
     const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];
     { StageTimer t_(ST_EMIT_KEYS, st, 1);
-    launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, gx, bs.is.keys[0], bs.is.vals[0]); }
+    launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, gx, bs.is.keys[0], bs.is.vals[0],
+             uint32_t(R), nr_out); }
     CG_LAUNCH_CHECK(s->debug, st);
     // stable sort by tile only
     int cur = 0;
     const int end_bit = int(tile_key_bits(uint32_t(tiles)));
     { StageTimer t_(ST_SORT, st, 0);
-    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st); }
+    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_n); }
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned((R + 255) / 256);
     { StageTimer t_(ST_GATHER, st, 1);
-    launch_k(gather_records, dim3(rb), dim3(256), 0, st, R, bs.is.keys[cur], bs.is.vals[cur], g, colors,
+    launch_k(gather_records, dim3(rb), dim3(256), 0, st, R, d_n, bs.is.keys[cur], bs.is.vals[cur], g, colors,
                                        s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
   }

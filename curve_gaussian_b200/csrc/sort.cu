@@ -32,8 +32,10 @@ constexpr uint32_t FLAG_INC = 2u;   // inclusive prefix published
 
 template <typename K>
 __global__ void __launch_bounds__(256)
-sort_histogram(const K* __restrict__ keys, int64_t R, int passes, int bpp, uint32_t* __restrict__ hist) {
+sort_histogram(const K* __restrict__ keys, int64_t R, const uint32_t* __restrict__ d_n, int passes, int bpp,
+               uint32_t* __restrict__ hist) {
   pdl_wait();
+  if (d_n) R = min(R, int64_t(*d_n));   // device-side count (capacity mode): R is only the capacity
   __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
   for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -82,9 +84,11 @@ template <typename K>
 __global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 4 ? 3 : 2)
 sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                   int64_t R, int shift, uint32_t dmask, const uint32_t* __restrict__ digit_base,
-                   uint32_t* __restrict__ ticket, uint32_t* __restrict__ status) {
+                   int64_t R, const uint32_t* __restrict__ d_n, int shift, uint32_t dmask,
+                   const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ ticket,
+                   uint32_t* __restrict__ status) {
   pdl_wait();
+  if (d_n) R = min(R, int64_t(*d_n));   // device-side count: the grid covers the capacity, surplus CTAs leave below
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SortSmem<K>& s = *reinterpret_cast<SortSmem<K>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,6 +101,7 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
   const uint32_t tile = s.tile_id;
   CG_SORT_TICK(0);
   const int64_t tile_base = int64_t(tile) * SORT_TILE;
+  if (tile_base >= R) return;   // uniform: tickets are handed out in order, so every live tile's predecessors are live
   const int64_t warp_base = tile_base + int64_t(warp) * (32 * SORT_ITEMS);
 
   K k[SORT_ITEMS];
@@ -246,7 +251,8 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
 }  // namespace
 
 template <typename K>
-int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf, bool debug, cudaStream_t stream) {
+int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf, bool debug, cudaStream_t stream,
+                     const uint32_t* d_n) {
   *out_buf = 0;
   if (R <= 0) return CG_OK;
   if (R >= (int64_t(1) << FLAG_SHIFT)) {
@@ -275,14 +281,14 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
 
   int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
   count_launches(2 + passes);
-  launch_k(sort_histogram<K>, dim3(hist_blocks), dim3(256), 0, stream, b.keys[0], R, passes, bpp, b.hist);
+  launch_k(sort_histogram<K>, dim3(hist_blocks), dim3(256), 0, stream, b.keys[0], R, d_n, passes, bpp, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
   launch_k(sort_scan_bins, dim3(passes), dim3(256), 0, stream, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
 
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
-    launch_k(sort_onesweep_pass<K>, dim3(unsigned(ntiles)), dim3(SORT_THREADS), sizeof(SortSmem<K>), stream, b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, bpp * p, dmask,
+    launch_k(sort_onesweep_pass<K>, dim3(unsigned(ntiles)), dim3(SORT_THREADS), sizeof(SortSmem<K>), stream, b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, d_n, bpp * p, dmask,
         b.hist + p * 256, b.ticket + p, b.status + size_t(p) * ntiles * 256);
     CG_LAUNCH_CHECK(debug, stream);
     cur ^= 1;
@@ -291,7 +297,7 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
   return CG_OK;
 }
 
-template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t);
-template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t);
+template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*);
+template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*);
 
 }  // namespace cg

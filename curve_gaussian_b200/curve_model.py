@@ -1,10 +1,9 @@
-"""Host-side mirror of the reference GaussianCurveModel's hot-path surface
-(scene/gaussian_curve_model.py:54-198): same attribute names, properties and
-`prepare_scaling_rot()`, with the sampling math running as the fused CUDA op in
-sampling.py. Topology surgery, optimizer bookkeeping and ply I/O (the rest of that
-727-line class) are host control logic outside the hot path and are
-not reimplemented; they only need `prepare_scaling_rot()` to keep working after
-they edit `_curve_points/_width/_opacity/_mask/is_bezier`, which it does.
+"""Host-side mirror of the reference GaussianCurveModel (scene/gaussian_curve_model.py): same attribute
+names, properties and `prepare_scaling_rot()`, with the sampling math running as the fused CUDA op in
+sampling.py (:54-198, the hot path). The training-time surgery on the curve set and the optimizer
+bookkeeping (:200-459) come from topology.CurveTopology; checkpoints and the on-disk formats (ply,
+parametric_edges.json) from curve_io. RANSAC curve merging (:462-640) and the mesh/point-cloud debug dumps
+(:643-727) are not carried over.
 """
 from __future__ import annotations
 
@@ -12,8 +11,9 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import sampling
+from . import curve_io, sampling
 from .knn import distCUDA2
+from .topology import CurveTopology
 
 
 def quaternion_to_matrix(quaternions: torch.Tensor) -> torch.Tensor:
@@ -35,7 +35,7 @@ def initialize_bezier_curves(points, bound, n_control_points=4):
                        dim=1)
 
 
-class GaussianCurveModel:
+class GaussianCurveModel(CurveTopology):
     def __init__(self, sh_degree=0, n_gaussians=12, optimizer_type="default", device="cuda"):
         self.active_sh_degree = 0
         self.max_sh_degree = sh_degree
@@ -52,6 +52,12 @@ class GaussianCurveModel:
         self._curve_points = torch.empty(0)
         self.is_bezier = torch.empty(0)
         self.max_radii2D = torch.empty(0)
+        self._features_dc = torch.empty(0)
+        self._features_rest = torch.empty(0)
+        self.xyz_gradient_accum = torch.empty(0)
+        self.denom = torch.empty(0)
+        self.optimizer = None
+        self.spatial_lr_scale = 0
         # activations of the base class (scene/gaussian_model.py:38-53)
         self.scaling_activation = torch.exp
         self.scaling_inverse_activation = torch.log
@@ -72,6 +78,11 @@ class GaussianCurveModel:
         self.is_bezier = (torch.ones(B, dtype=torch.bool, device=dev) if is_bezier is None
                           else is_bezier.to(dev).bool())
         self.max_radii2D = torch.zeros(B * self.n_gaussians, device=dev)
+        # per-sample SH feature slots of the reference (:159-166); render() never reads them (colours are a
+        # constant 1), they exist so that the optimizer groups and checkpoints keep the reference's layout
+        k = (self.max_sh_degree + 1) ** 2 - 1
+        self._features_dc = nn.Parameter(torch.zeros((B, self.n_gaussians, 1, 1), device=dev).requires_grad_(True))
+        self._features_rest = nn.Parameter(torch.zeros((B, self.n_gaussians, k, 1), device=dev).requires_grad_(True))
         self.prepare_scaling_rot()
         return self
 
@@ -90,6 +101,10 @@ class GaussianCurveModel:
 
     # ---- the hot path -----------------------------------------------------
     def prepare_scaling_rot(self, eps=1e-8):
+        # drop the previous iteration's autograd graph BEFORE building the new one: while the old sampled
+        # tensors are alive they keep the parameters' AccumulateGrad nodes (and the stream those were created
+        # on) alive, which ties a step captured into a CUDA graph to the stream of an earlier eager step
+        self._xyz = self._rotation = self._scaling = None
         xyz, rot, scaling = sampling.sample_curves(self._curve_points, self._width, self.is_bezier,
                                                    self.sample_t.view(-1))
         self._xyz, self._rotation, self._scaling = xyz, rot, scaling
@@ -135,3 +150,19 @@ class GaussianCurveModel:
 
     def parameters(self):
         return [self._curve_points, self._width, self._opacity, self._mask]
+
+    # ---- checkpoints and on-disk formats (curve_io) -------------------------
+    def capture(self):
+        return curve_io.capture(self)
+
+    def restore(self, model_args, training_args=None):
+        return curve_io.restore(self, model_args, training_args)
+
+    def save_ply(self, path):
+        return curve_io.save_gaussians_ply(self, path)
+
+    def save_curves(self, path):
+        return curve_io.save_curves(self, path)
+
+    def load_curves(self, path):
+        return curve_io.load_curves(self, path)

@@ -68,10 +68,144 @@ def _bytes(n: int, device) -> torch.Tensor:
     return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
 
 
-def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, all_maps):
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def _pinned_i32(n: int) -> torch.Tensor:
+    t = torch.zeros(n, dtype=torch.int32)
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+class CapacityOverflow(_lib.CurveGSError):
+    """A sync-free forward met more tile-instances than its binning capacity: that step's outputs are not the
+    reference's. The policy has already grown the capacity; repeat the step."""
+
+
+class CapacityBinning:
+    """Sync-free binning policy.
+
+    The reference reads the tile-instance count R back to the host in every forward to size its binning
+    buffers (rasterizer_impl.cu:283-291); that round trip is what keeps a small scene host-bound and what
+    makes the step impossible to capture in a CUDA graph. With this policy active (`capacity_binning()`),
+    the first forward of each (P, W, H) shape runs the exact path to learn R; later ones call
+    `cg_raster_fwd_capacity` with buffers sized for `headroom * max R seen`, never touch the host, and leave
+    {R, overflow} in a pinned host slot behind the step. `poll()` (non-blocking, call it once per iteration)
+    or `check()` (after the caller synchronised anyway) raise `CapacityOverflow` for a step that overflowed
+    and keep the capacity tracking the largest R observed.
+    """
+
+    def __init__(self, headroom: float = 1.3, granule: int = 1 << 16):
+        self.headroom = float(headroom)
+        self.granule = int(granule)
+        self.caps: dict = {}          # (P, W, H) -> capacity in tile-instances
+        self.max_seen: dict = {}      # (P, W, H) -> largest R observed
+        self._pending: list = []      # (key, pinned int32[2], event, capacity used)
+        self._free: list = []
+        self._static: dict = {}       # key -> pinned int32[2] refreshed by graph replays
+        self.overflows = 0
+
+    def _round(self, R: int) -> int:
+        g = self.granule
+        return max(g, (int(R * self.headroom) + g - 1) // g * g)
+
+    def learn(self, key, R: int) -> None:
+        if key not in self._static and not _capturing():
+            # (pinned allocations are not allowed while a capture is open, so the slot exists beforehand)
+            self._static[key] = _pinned_i32(3)
+        if R > self.max_seen.get(key, -1):
+            self.max_seen[key] = int(R)
+            if self._round(R) > self.caps.get(key, 0):
+                self.caps[key] = self._round(R)
+
+    def capacity(self, key):
+        return self.caps.get(key)
+
+    def observe(self, key, counter: torch.Tensor, cap: int) -> None:
+        """Queue the device counter {R, overflow} of a capacity forward for a later poll()/check()."""
+        if _capturing():
+            # inside a CUDA graph: a fixed pinned slot, rewritten by every replay, read by check()
+            slot = self._static[key]
+            slot[2] = cap
+            slot[:2].copy_(counter, non_blocking=True)
+            return
+        slot = self._free.pop() if self._free else _pinned_i32(2)
+        slot.copy_(counter, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((key, slot, ev, cap))
+
+    def _account(self, key, R: int, over: int, cap: int) -> bool:
+        self.learn(key, R)
+        if over:
+            self.overflows += 1
+        return bool(over)
+
+    def poll(self, block: bool = False) -> None:
+        """Account for every finished capacity forward; raise CapacityOverflow if one of them overflowed."""
+        bad = None
+        keep = []
+        for key, slot, ev, cap in self._pending:
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                keep.append((key, slot, ev, cap))
+                continue
+            R, over = int(slot[0]), int(slot[1])
+            self._free.append(slot)
+            if self._account(key, R, over, cap):
+                bad = (key, R, cap)
+        self._pending = keep
+        if bad is not None:
+            raise CapacityOverflow(f"{bad[1]} tile-instances exceeded the binning capacity {bad[2]} for "
+                                   f"(P, W, H) = {bad[0]}; the capacity was raised, repeat the step")
+
+    def check(self) -> None:
+        """After the caller synchronised: poll(block=True) plus the slots written by CUDA-graph replays."""
+        self.poll(block=True)
+        for key, slot in self._static.items():
+            R, over, cap = int(slot[0]), int(slot[1]), int(slot[2])
+            slot[1] = 0   # reported once
+            if self._account(key, R, over, cap):
+                raise CapacityOverflow(f"{R} tile-instances exceeded the captured binning capacity {cap} for "
+                                       f"(P, W, H) = {key}; re-capture the step (the capacity was raised)")
+
+
+_policy: CapacityBinning | None = None
+
+
+class capacity_binning:
+    """Context manager / switch: `with capacity_binning() as pol: ...` or `pol = capacity_binning().enable()`."""
+
+    def __init__(self, policy: CapacityBinning | None = None, **kw):
+        self.policy = policy or CapacityBinning(**kw)
+        self._prev = None
+
+    def enable(self) -> CapacityBinning:
+        global _policy
+        self._prev, _policy = _policy, self.policy
+        return self.policy
+
+    def disable(self) -> None:
+        global _policy
+        _policy = self._prev
+
+    def __enter__(self) -> CapacityBinning:
+        return self.enable()
+
+    def __exit__(self, *exc):
+        self.disable()
+        return False
+
+
+def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, all_maps,
+                          capacity=None):
     """The `_C.rasterize_gaussians` equivalent (rasterize_points.cu:35-130).
 
     Returns (num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer, invdepths, out_all_map).
+    With `capacity` (an int, or the active CapacityBinning policy's choice) the forward does not read R
+    back: `num_rendered` is then the CAPACITY the buffers were sized for (pass it on to the backward) and the
+    true count is in `rasterize_forward_raw.last_counter` (device int32[2] = {R, overflow}).
     """
     lib = _lib.load()
     if means3D.ndim != 2 or means3D.shape[1] != 3:
@@ -108,6 +242,30 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
     if P > 0 and colors is None:
         raise _lib.CurveGSError("colors_precomp is required (the SH path is not part of the curve pipeline)")
 
+    key = (P, W, H)
+    if capacity is None and _policy is not None:
+        capacity = _policy.capacity(key)
+        if capacity is None and _capturing():
+            raise _lib.CurveGSError(f"no binning capacity known for (P, W, H) = {key}: run the step once outside "
+                                    "the CUDA graph capture (or CapacityBinning.learn(key, R)) first")
+    if capacity is not None:
+        cap = int(capacity)
+        bin_keep = _bytes(lib.cg_raster_bin_keep_bytes(cap), dev)
+        bin_scratch = _bytes(lib.cg_raster_bin_scratch_bytes(P, cap), dev)
+        counter = torch.empty(2, dtype=torch.int32, device=dev)
+        with _lib.on_device(dev):
+            _lib.check(lib.cg_raster_fwd_capacity(
+                C.byref(s), P, cap, _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales), _lib.ptr(rotations),
+                _lib.ptr(cov3D), _lib.ptr(colors), _lib.ptr(amap), _lib.ptr(radii), geom.data_ptr(), geom.numel(),
+                img.data_ptr(), bin_keep.data_ptr(), bin_scratch.data_ptr(), color.data_ptr(), invdepth.data_ptr(),
+                out_all_map.data_ptr(), counter.data_ptr(), stream), "cg_raster_fwd_capacity")
+        if _policy is not None:
+            _policy.observe(key, counter, cap)
+        rasterize_forward_raw.last_scratch = bin_scratch
+        rasterize_forward_raw.last_R = cap
+        rasterize_forward_raw.last_counter = counter
+        return cap, color, radii, geom, bin_keep, img, invdepth, out_all_map
+
     R = C.c_int64(0)
     with _lib.on_device(dev):
         _lib.check(lib.cg_raster_fwd_geom(C.byref(s), P, _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales),
@@ -123,6 +281,9 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
     # keep scratch reachable for debug_fetch of the sorted keys
     rasterize_forward_raw.last_scratch = bin_scratch
     rasterize_forward_raw.last_R = R
+    rasterize_forward_raw.last_counter = None
+    if _policy is not None:
+        _policy.learn(key, R)
     return R, color, radii, geom, bin_keep, img, invdepth, out_all_map
 
 

@@ -1,0 +1,265 @@
+"""Curve-set surgery and optimizer bookkeeping of the reference GaussianCurveModel.
+
+These are the calls train.py makes every 500-2000 iterations between hot-path steps
+(scene/gaussian_curve_model.py:200-456; scene/gaussian_model.py:460-533 for the optimizer edits). They only
+rearrange the per-curve tensors `_curve_points/_width/_opacity/_mask/is_bezier` (+ Adam moments); everything
+runs as a handful of whole-tensor device ops, no per-curve host loop, and ends with `prepare_scaling_rot()` so
+the hot path sees the new curve set. Method names, arguments and results follow the reference.
+
+Not carried over: `merge_curves` / `fit_curve_to_line` (RANSAC line fits through skimage + the repo's
+edge_extraction package on the host) - a different subsystem, see DESIGN.md.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional
+
+import torch
+from torch import nn
+
+
+def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """Log-linear learning-rate decay with an optional eased-in start (utils/general_utils.py:99-133)."""
+    log_i = math.log(lr_init) if lr_init > 0 else 0.0
+    log_f = math.log(lr_final) if lr_final > 0 else 0.0
+
+    def helper(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        rate = 1.0
+        if lr_delay_steps > 0:
+            rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+        t = min(max(step / max_steps, 0), 1)
+        return rate * math.exp(log_i * (1 - t) + log_f * t)
+
+    return helper
+
+
+def de_casteljau_split(curves: torch.Tensor, t: torch.Tensor, is_bezier: torch.Tensor):
+    """Split every curve at its own parameter t into (left, right) control polygons, each (K,4,3).
+
+    Cubic Beziers by De Casteljau; straight segments (is_bezier False) are cut at the point (1-t)P0 + tP3 and
+    both halves get evenly spaced inner control points (gaussian_curve_model.py:389-424). t is (K,1).
+    """
+    p0, p1, p2, p3 = curves.unbind(1)
+    s = 1 - t
+    q0, q1, q2 = s * p0 + t * p1, s * p1 + t * p2, s * p2 + t * p3
+    r0, r1 = s * q0 + t * q1, s * q1 + t * q2
+    mid = s * r0 + t * r1
+    left = torch.stack([p0, q0, r0, mid], dim=1)
+    right = torch.stack([mid, r1, q2, p3], dim=1)
+    if bool(is_bezier.all()):
+        return left, right
+    cut = s * p0 + t * p3
+    left_s = torch.stack([p0, (2 / 3) * p0 + (1 / 3) * cut, (1 / 3) * p0 + (2 / 3) * cut, cut], dim=1)
+    right_s = torch.stack([cut, (2 / 3) * cut + (1 / 3) * p3, (1 / 3) * cut + (2 / 3) * p3, p3], dim=1)
+    sel = is_bezier[:, None, None]
+    return torch.where(sel, left, left_s), torch.where(sel, right, right_s)
+
+
+def de_casteljau_trim(curves, from_t, end_t, is_bezier):
+    """Keep the part after from_t, then the part of THAT curve before end_t (gaussian_curve_model.py:367-370;
+    end_t is applied in the re-parametrised remainder, as the reference does)."""
+    _, rest = de_casteljau_split(curves, from_t, is_bezier)
+    kept, _ = de_casteljau_split(rest, end_t, is_bezier)
+    return kept
+
+
+def resample_mask_rows(mask: torch.Tensor, start: torch.Tensor, end: torch.Tensor) -> torch.Tensor:
+    """Row b of the (B,n) mask, restricted to [start_b, end_b], stretched back to n samples with the
+    half-pixel-centre linear rule of `F.interpolate(mode='bilinear', align_corners=False)` - all rows at once
+    (the reference loops over the curves, gaussian_curve_model.py:446-450)."""
+    B, n = mask.shape
+    length = (end - start + 1).to(mask.dtype)                      # source samples per row
+    i = torch.arange(n, device=mask.device, dtype=mask.dtype)[None, :]
+    src = ((i + 0.5) * (length[:, None] / n) - 0.5).clamp_min(0.0)
+    lo = src.floor().long()
+    lo = torch.minimum(lo, (end - start)[:, None])
+    hi = torch.minimum(lo + 1, (end - start)[:, None])
+    w = src - lo.to(mask.dtype)
+    a = torch.gather(mask, 1, start[:, None] + lo)
+    b = torch.gather(mask, 1, start[:, None] + hi)
+    return (1 - w) * a + w * b
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Adam surgery: every param group holds exactly one tensor (gaussian_curve_model.py:203-210)
+def _edit_groups(optimizer, names, new_param: Callable[[str, torch.Tensor], torch.Tensor],
+                 new_moment: Callable[[str, torch.Tensor, torch.Tensor], torch.Tensor]) -> Dict[str, nn.Parameter]:
+    out = {}
+    for group in optimizer.param_groups:
+        name = group["name"]
+        if names is not None and name not in names:
+            continue
+        old = group["params"][0]
+        state = optimizer.state.pop(old, None)
+        new = nn.Parameter(new_param(name, old.detach()).requires_grad_(True))
+        if state is not None and "exp_avg" in state:
+            state["exp_avg"] = new_moment(name, state["exp_avg"], new)
+            state["exp_avg_sq"] = new_moment(name, state["exp_avg_sq"], new)
+        if state is not None:
+            optimizer.state[new] = state
+        group["params"][0] = new
+        out[name] = new
+    return out
+
+
+class CurveTopology:
+    """Mixin for GaussianCurveModel: the reference's training-time surgery on the curve set."""
+
+    _GROUPS = (("f_dc", "_features_dc"), ("f_rest", "_features_rest"), ("opacity", "_opacity"), ("width", "_width"),
+               ("curve_points", "_curve_points"), ("mask", "_mask"))
+
+    # ---- optimizer -----------------------------------------------------------------------------------
+    def training_setup(self, training_args):
+        """Adam over the six per-curve tensors with the reference's group names and rates
+        (gaussian_curve_model.py:200-232); the curve-point rate follows `update_learning_rate`."""
+        dev = self._curve_points.device
+        P = self._curve_points.shape[0] * self.n_gaussians
+        self.denom = torch.zeros((P, 1), device=dev)
+        self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
+        g = lambda k, d=0.0: getattr(training_args, k, d)
+        rates = {"f_dc": g("feature_lr", 0.0025), "f_rest": g("feature_lr", 0.0025) / 20.0, "opacity": g("opacity_lr", 0.05),
+                 "width": g("scaling_lr", 0.005), "curve_points": g("lr_curve_points_init", 0.00016),
+                 "mask": g("mask_lr", 0.01)}
+        groups = [{"params": [getattr(self, attr)], "lr": rates[name], "name": name} for name, attr in self._GROUPS]
+        self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        self.curve_scheduler_args = get_expon_lr_func(
+            lr_init=g("lr_curve_points_init", 0.00016), lr_final=g("lr_curve_points_final", 0.0000016),
+            lr_delay_mult=g("position_lr_delay_mult", 0.01), max_steps=g("position_lr_max_steps", 30000))
+        return self.optimizer
+
+    def update_learning_rate(self, iteration):
+        for group in self.optimizer.param_groups:
+            if group["name"] == "curve_points":
+                group["lr"] = self.curve_scheduler_args(iteration)
+                return group["lr"]
+
+    def _adopt(self, tensors: Dict[str, nn.Parameter]) -> None:
+        for name, attr in self._GROUPS:
+            if name in tensors:
+                setattr(self, attr, tensors[name])
+
+    def _prune_optimizer(self, keep):
+        return _edit_groups(self.optimizer, None, lambda _, p: p[keep], lambda _, m, __: m[keep])
+
+    def cat_tensors_to_optimizer(self, tensors_dict):
+        return _edit_groups(self.optimizer, None, lambda k, p: torch.cat((p, tensors_dict[k]), dim=0),
+                            lambda k, m, _: torch.cat((m, torch.zeros_like(tensors_dict[k])), dim=0))
+
+    def replace_tensor_to_optimizer(self, tensor, name):
+        return _edit_groups(self.optimizer, (name,), lambda _, __: tensor, lambda _, __, new: torch.zeros_like(new))
+
+    def add_densification_stats(self, viewspace_point_tensor, update_filter):
+        """scene/gaussian_model.py:618-620 (update_filter: boolean (P,) or index tensor)."""
+        g = viewspace_point_tensor.grad
+        self.xyz_gradient_accum[update_filter] += torch.norm(g[update_filter, :2], dim=-1, keepdim=True)
+        self.denom[update_filter] += 1
+
+    # ---- opacity resets ---------------------------------------------------------------------------------
+    def reset_opacity(self):
+        new = self.inverse_opacity_activation(torch.clamp_max(self.get_curve_opacity.detach(), 0.1))
+        self._adopt(self.replace_tensor_to_optimizer(new, "opacity"))
+
+    def fix_opacity(self):
+        new = self.inverse_opacity_activation(torch.clamp_min(self.get_curve_opacity.detach(), 0.6))
+        self._adopt(self.replace_tensor_to_optimizer(new, "opacity"))
+        self._opacity.requires_grad = False
+        for group in self.optimizer.param_groups:
+            if group["name"] == "opacity":
+                group["lr"] = 0.0
+
+    # ---- prune / append -----------------------------------------------------------------------------------
+    def prune_curves(self, mask):
+        """Drop the curves where mask is True, with their Adam moments and per-Gaussian statistics
+        (gaussian_curve_model.py:283-305)."""
+        keep = ~mask
+        self._adopt(self._prune_optimizer(keep))
+        keep_pts = keep[:, None].expand(-1, self.n_gaussians).reshape(-1)
+        self.xyz_gradient_accum = self.xyz_gradient_accum[keep_pts]
+        self.denom = self.denom[keep_pts]
+        self.is_bezier = self.is_bezier[keep]
+        self.max_radii2D = self.max_radii2D[keep_pts]
+        tmp = getattr(self, "tmp_radii", None)
+        if tmp is not None and tmp.shape[0] == keep_pts.shape[0]:
+            self.tmp_radii = tmp[keep_pts]
+        self.prepare_scaling_rot()
+
+    def densification_postfix(self, new_curve_points, new_features_dc, new_features_rest, new_opacities, new_widths,
+                              new_masks, new_is_bezier):
+        """Append curves; the per-Gaussian statistics restart from zero (gaussian_curve_model.py:307-326)."""
+        self._adopt(self.cat_tensors_to_optimizer({
+            "curve_points": new_curve_points, "f_dc": new_features_dc, "f_rest": new_features_rest,
+            "opacity": new_opacities, "width": new_widths, "mask": new_masks}))
+        self.is_bezier = torch.cat((self.is_bezier, new_is_bezier))
+        dev = self._curve_points.device
+        P = self._curve_points.shape[0] * self.n_gaussians
+        self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
+        self.denom = torch.zeros((P, 1), device=dev)
+        self.max_radii2D = torch.zeros(P, device=dev)
+
+    def densify_and_split_curve(self, selected, t, N=2):
+        """Replace every selected curve by its two halves at parameter t ((K,1), K = selected.sum());
+        the halves inherit width, opacity and mask (gaussian_curve_model.py:330-347)."""
+        assert N == 2
+        k = int(selected.sum())
+        rep = lambda x: x.detach()[selected].repeat(N, *([1] * (x.dim() - 1)))
+        left, right = de_casteljau_split(self._curve_points.detach()[selected], t, self.is_bezier[selected])
+        self.densification_postfix(torch.cat((left, right), dim=0), rep(self._features_dc), rep(self._features_rest),
+                                   rep(self._opacity), rep(self._width), rep(self._mask), self.is_bezier[selected].repeat(N))
+        gone = torch.cat((selected, torch.zeros(N * k, device=selected.device, dtype=torch.bool)))
+        self.prune_curves(gone)
+
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, radii):
+        """Split each curve whose largest mean screen-space gradient reaches max_grad at the sample where it
+        occurs, then drop curves fainter than min_opacity (gaussian_curve_model.py:349-365)."""
+        grads = self.xyz_gradient_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        self.tmp_radii = radii
+        per_curve = torch.norm(grads.view(-1, self.n_gaussians, grads.shape[-1]), dim=-1)
+        top, where = per_curve.max(dim=1)
+        selected = top >= max_grad
+        if bool(selected.any()):
+            self.densify_and_split_curve(selected, self.sample_t[where[selected]].squeeze(-1))
+        self.prune_curves((self.get_curve_opacity < min_opacity).reshape(-1))
+
+    def curve_split_curvature(self, threshold_angle=20, threshold_radian_skip=30):
+        """Split at the sharpest bend the curves whose main axis turns by more than threshold_angle degrees
+        between neighbouring samples (or threshold_radian_skip between samples two apart)
+        (gaussian_curve_model.py:372-387)."""
+        n = self.n_gaussians
+        axis = self.get_rotation_matrix[..., 0].detach().view(-1, n, 3)
+        ang = torch.acos((axis[:, :-1] * axis[:, 1:]).sum(-1).clamp(-1, 1))
+        ang2 = torch.acos((axis[:, :-2] * axis[:, 2:]).sum(-1).clamp(-1, 1))
+        split = (ang.max(dim=-1).values > math.radians(threshold_angle)) | \
+                (ang2.max(dim=-1).values > math.radians(threshold_radian_skip))
+        where = ang.argmax(dim=-1)
+        end_t = self.sample_t[where] + 0.5 / n
+        self.densify_and_split_curve(split, end_t[split].squeeze(-1))
+        self.prepare_scaling_rot()
+
+    def only_prune(self, min_opacity, mask_threshold):
+        """Drop curves that are fully masked out, too faint, or shorter than 1e-2 in summed sample scale
+        (gaussian_curve_model.py:427-435)."""
+        masked = (torch.sigmoid(self._mask.detach()) <= mask_threshold).all(dim=1).reshape(-1)
+        faint = (self.get_curve_opacity < min_opacity).reshape(-1)
+        short = self._scaling[:, 0].detach().reshape(-1, self.n_gaussians).sum(-1) < 1e-2
+        self.prune_curves(masked | faint | short)
+
+    def mask_trim_split(self, mask_threshold):
+        """Cut the masked-out samples off both ends of every curve and stretch the surviving part of its mask
+        logits back over all n samples (gaussian_curve_model.py:437-459)."""
+        n = self.n_gaussians
+        m = self._mask.detach().view(-1, n)
+        valid = torch.sigmoid(m) > mask_threshold
+        start = valid.int().argmax(dim=1)
+        end = n - 1 - valid.flip(1).int().argmax(dim=1)
+        t = self.sample_t.view(-1)
+        from_t = (t[start] - 0.5 / n)[:, None]
+        end_t = (t[end] + 0.5 / n)[:, None]
+        trimmed = de_casteljau_trim(self._curve_points.detach(), from_t, end_t, self.is_bezier)
+        touched = (start != 0) | (end != n - 1)
+        new_mask = torch.where(touched[:, None], resample_mask_rows(m, start, torch.maximum(end, start)), m)
+        self._adopt(self.replace_tensor_to_optimizer(new_mask.view(-1, n, 1).contiguous(), "mask"))
+        self._adopt(self.replace_tensor_to_optimizer(trimmed.contiguous(), "curve_points"))
+        self.prepare_scaling_rot()

@@ -47,6 +47,8 @@ const char* cg_last_error(void);
  * since load, and optional per-stage device timing with CUDA events recorded on the
  * launch stream. cg_profile_read synchronizes on the recorded events. */
 uint64_t cg_launch_count(void);
+/* Programmatic dependent launch of the library's kernels (on by default); a debugging switch. */
+void cg_set_pdl(int on);
 void cg_profile_enable(int on);
 void cg_profile_reset(void);
 int cg_profile_stage_count(void);
@@ -114,6 +116,27 @@ int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R,
                         void* bin_keep, void* bin_scratch,
                         float* out_color, float* out_invdepth, float* out_all_map,
                         void* stream);
+
+/* Forward without the host round trip (both stages in one call; CUDA-graph capturable: no
+ * host synchronisation, no host allocation). The reference reads the number of tile-instances R
+ * back to size its binning buffers (rasterizer_impl.cu:283-291); here the caller sizes bin_keep and
+ * bin_scratch for a CAPACITY of R_cap instances (cg_raster_bin_keep_bytes(R_cap),
+ * cg_raster_bin_scratch_bytes(P, R_cap)) and the true R stays on the device: every R-sized
+ * kernel is launched for the capacity and reads the count itself. num_rendered_dev (DEVICE,
+ * 2 x uint32) receives {R, overflow}; with overflow == 1 (R > R_cap) the farthest R - R_cap
+ * instances were dropped and the outputs are not the reference's: the caller checks the
+ * counter once the stream has passed this call (it may copy it to pinned memory behind the
+ * call) and repeats the step with a larger capacity. When R <= R_cap every output, the saved
+ * state and the later cg_raster_bwd (called with R = R_cap) are bit-identical to the
+ * cg_raster_fwd_geom + cg_raster_fwd_blend pair. */
+int cg_raster_fwd_capacity(const cg_raster_settings* s, int64_t P, int64_t R_cap,
+                           const float* means3D, const float* opacities, const float* scales,
+                           const float* rotations, const float* cov3D_precomp,
+                           const float* colors, const float* all_map,
+                           int32_t* radii, void* geom, size_t geom_bytes, void* img,
+                           void* bin_keep, void* bin_scratch,
+                           float* out_color, float* out_invdepth, float* out_all_map,
+                           uint32_t* num_rendered_dev, void* stream);
 
 /* Backward. dL_dinvdepth / dL_dall_map may be NULL (treated as zeros, which is
  * what autograd materialises for unused outputs). Gradient outputs follow

@@ -1,0 +1,47 @@
+"""CPU: host logic of the sync-free binning policy (rasterizer.CapacityBinning) - no kernels involved."""
+import pytest
+
+from curve_gaussian_b200 import rasterizer as rz
+
+
+def test_capacity_tracks_the_largest_count_with_headroom():
+    pol = rz.CapacityBinning(headroom=1.5, granule=1000)
+    key = (100, 64, 48)
+    assert pol.capacity(key) is None           # unknown shape: the first forward takes the exact path
+    pol.learn(key, 10_000)
+    assert pol.capacity(key) == 15_000
+    pol.learn(key, 4_000)                       # smaller counts never shrink it
+    assert pol.capacity(key) == 15_000 and pol.max_seen[key] == 10_000
+    pol.learn(key, 10_001)
+    assert pol.capacity(key) == 16_000          # rounded up to the granule
+    pol.learn((7, 8, 9), 1)
+    assert pol.capacity((7, 8, 9)) == 1000      # at least one granule
+    assert key in pol._static                   # the pinned slot graph replays write to exists before any capture
+
+
+def test_accounting_raises_once_per_overflow_and_grows():
+    pol = rz.CapacityBinning(headroom=1.25, granule=64)
+    key = (10, 32, 32)
+    pol.learn(key, 640)
+    cap = pol.capacity(key)
+    assert cap == 832
+    assert pol._account(key, 700, 0, cap) is False and pol.capacity(key) == 896
+    assert pol._account(key, 5000, 1, cap) is True
+    assert pol.overflows == 1 and pol.capacity(key) >= 5000
+    # slots written by graph replays are reported once
+    slot = pol._static[key]
+    slot[0], slot[1], slot[2] = 9000, 1, 6272
+    with pytest.raises(rz.CapacityOverflow):
+        pol.check()
+    pol.check()
+    assert pol.capacity(key) >= 9000
+
+
+def test_switch_nests_and_restores():
+    assert rz._policy is None
+    with rz.capacity_binning(headroom=2.0) as a:
+        assert rz._policy is a
+        with rz.capacity_binning() as b:
+            assert rz._policy is b and b is not a
+        assert rz._policy is a
+    assert rz._policy is None
