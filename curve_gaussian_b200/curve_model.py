@@ -69,12 +69,13 @@ class GaussianCurveModel(CurveTopology):
     def create_from_curves(self, curve_points, width, opacity_logit, is_bezier=None, mask=None):
         dev = self.sample_t.device
         B = curve_points.shape[0]
-        self._curve_points = nn.Parameter(curve_points.to(dev).float().contiguous().requires_grad_(True))
-        self._width = nn.Parameter(width.to(dev).float().view(B, 1).contiguous().requires_grad_(True))
-        self._opacity = nn.Parameter(opacity_logit.to(dev).float().view(B, 1).contiguous().requires_grad_(True))
+        own = lambda t, *shape: nn.Parameter(t.detach().to(dev, torch.float32).reshape(*shape).clone().requires_grad_(True))
+        self._curve_points = own(curve_points, B, 4, 3)
+        self._width = own(width, B, 1)
+        self._opacity = own(opacity_logit, B, 1)
         if mask is None:
             mask = torch.ones((B, self.n_gaussians, 1), device=dev)
-        self._mask = nn.Parameter(mask.to(dev).float().contiguous().requires_grad_(True))
+        self._mask = own(mask, B, self.n_gaussians, 1)
         self.is_bezier = (torch.ones(B, dtype=torch.bool, device=dev) if is_bezier is None
                           else is_bezier.to(dev).bool())
         self.max_radii2D = torch.zeros(B * self.n_gaussians, device=dev)

@@ -1,0 +1,207 @@
+"""CPU: curve-set surgery, optimizer bookkeeping, checkpoints and on-disk formats against
+golden vectors produced by the reference's own methods (tests/golden/make_topology_golden.py). The model's
+sampling op is CUDA-only, so here `prepare_scaling_rot` is routed to the torch restatement in oracle/ - the
+surgery under test only rearranges per-curve tensors."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from curve_gaussian_b200 import curve_io, synth, topology
+from curve_gaussian_b200.curve_model import GaussianCurveModel
+from oracle import torch_ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class CpuModel(GaussianCurveModel):
+    def prepare_scaling_rot(self, eps=1e-8):
+        self._xyz, self._rotation, self._scaling = torch_ref.sample_curves(self._curve_points, self._width,
+                                                                           self.is_bezier, self.n_gaussians)
+
+
+class Args:
+    feature_lr = 0.0025
+    opacity_lr = 0.05
+    scaling_lr = 0.005
+    mask_lr = 0.01
+    lr_curve_points_init = 0.00016
+    lr_curve_points_final = 0.0000016
+    position_lr_delay_mult = 0.01
+    position_lr_max_steps = 30000
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, f"topology_{name}.npz")).items()}
+
+
+def model_from(d):
+    t = lambda k: torch.from_numpy(d["in_" + k])
+    n = int(d["n"])
+    m = CpuModel(0, n_gaussians=n, device="cpu").create_from_curves(t("curve_points"), t("width"), t("opacity"),
+                                                                    t("is_bezier"), t("mask"))
+    m.training_setup(Args())
+    for group in m.optimizer.param_groups:
+        p = group["params"][0]
+        st = {"step": torch.tensor(1.0), "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+        if "in_exp_avg_" + group["name"] in d:
+            st["exp_avg"] = t("exp_avg_" + group["name"]).clone()
+            st["exp_avg_sq"] = t("exp_avg_sq_" + group["name"]).clone()
+        m.optimizer.state[p] = st
+    m.xyz_gradient_accum, m.denom = t("accum").clone(), t("denom").clone()
+    m.max_radii2D = t("max_radii2D").clone()
+    return m
+
+
+def check(m, d, mask_tol=0.0):
+    t = lambda k: torch.from_numpy(d["out_" + k])
+    assert m._curve_points.shape == t("curve_points").shape
+    assert torch.equal(m.is_bezier, t("is_bezier"))
+    for name, attr in (("curve_points", "_curve_points"), ("width", "_width"), ("opacity", "_opacity")):
+        assert torch.equal(getattr(m, attr).detach(), t(name)), name
+    if mask_tol:
+        assert (m._mask.detach() - t("mask")).abs().max() <= mask_tol
+    else:
+        assert torch.equal(m._mask.detach(), t("mask"))
+    assert torch.equal(m.xyz_gradient_accum, t("accum")) and torch.equal(m.denom, t("denom"))
+    assert torch.equal(m.max_radii2D, t("max_radii2D"))
+    for group in m.optimizer.param_groups:
+        key = "out_exp_avg_" + group["name"]
+        if key in d:
+            st = m.optimizer.state[group["params"][0]]
+            assert torch.equal(st["exp_avg"], torch.from_numpy(d[key])), key
+            assert torch.equal(st["exp_avg_sq"], torch.from_numpy(d["out_exp_avg_sq_" + group["name"]])), key
+            assert group["params"][0] is getattr(m, dict(m._GROUPS)[group["name"]])
+    assert m._xyz.shape[0] == m._curve_points.shape[0] * m.n_gaussians      # re-sampled after the surgery
+
+
+def test_de_casteljau_split_and_trim_match_reference_bits():
+    d = np.load(os.path.join(GOLD, "topology_split.npz"))
+    cp, isb, t, t2 = (torch.from_numpy(d[k]) for k in ("cp", "is_bezier", "t", "t2"))
+    left, right = topology.de_casteljau_split(cp, t, isb)
+    assert torch.equal(left, torch.from_numpy(d["left"])) and torch.equal(right, torch.from_numpy(d["right"]))
+    assert torch.equal(topology.de_casteljau_trim(cp, t * 0.5, t2, isb), torch.from_numpy(d["trimmed"]))
+    all_b = torch.ones_like(isb)
+    lb, rb = topology.de_casteljau_split(cp, t, all_b)
+    assert torch.equal(lb, torch.from_numpy(d["left_b"])) and torch.equal(rb, torch.from_numpy(d["right_b"]))
+    # the two halves of a Bezier trace the original curve: B_left(u) = B(t u), B_right(u) = B(t + (1-t) u)
+    u = torch.linspace(0, 1, 7)[:, None, None].double()
+    bez = lambda c, s: ((1 - s) ** 3 * c[:, 0] + 3 * (1 - s) ** 2 * s * c[:, 1] + 3 * (1 - s) * s ** 2 * c[:, 2] + s ** 3 * c[:, 3])
+    c64, t64 = cp.double(), t.double()[None, :, :]
+    assert (bez(lb.double(), u) - bez(c64, t64 * u)).abs().max() < 1e-6
+    assert (bez(rb.double(), u) - bez(c64, t64 + (1 - t64) * u)).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["densify", "curvature", "only_prune", "reset_opacity", "fix_opacity"])
+def test_surgery_matches_reference(name):
+    d = load(name)
+    m = model_from(d)
+    n_before = m._curve_points.shape[0]
+    {"densify": lambda: m.densify_and_prune(2.5e-4, 0.35, 1.0, 20, torch.ones(m._xyz.shape[0])),
+     "curvature": lambda: m.curve_split_curvature(threshold_angle=6, threshold_radian_skip=10),
+     "only_prune": lambda: m.only_prune(0.4, 0.6),
+     "reset_opacity": m.reset_opacity,
+     "fix_opacity": m.fix_opacity}[name]()
+    check(m, d)
+    if name in ("densify", "curvature"):
+        assert m._curve_points.shape[0] > n_before
+    if name == "fix_opacity":
+        assert not m._opacity.requires_grad
+        assert [g["lr"] for g in m.optimizer.param_groups if g["name"] == "opacity"] == [0.0]
+    # the optimizer still steps on the edited groups
+    for p in m.parameters():
+        if p.requires_grad:
+            p.grad = torch.ones_like(p)
+    m.optimizer.step()
+
+
+def test_mask_trim_split_matches_reference():
+    d = load("mask_trim")
+    m = model_from(d)
+    m.mask_trim_split(0.7)
+    check(m, d, mask_tol=2e-6)        # one vectorised resampling instead of F.interpolate per curve
+    assert (torch.from_numpy(d["in_curve_points"]) != m._curve_points.detach()).any()
+
+
+def test_resample_mask_rows_is_bilinear_interpolate():
+    g = torch.Generator().manual_seed(0)
+    n = 12
+    mask = torch.randn(30, n, generator=g)
+    start = torch.randint(0, n, (30,), generator=g)
+    end = torch.minimum(start + torch.randint(0, n, (30,), generator=g), torch.tensor(n - 1))
+    got = topology.resample_mask_rows(mask, start, end)
+    for b in range(30):
+        src = mask[b, start[b]:end[b] + 1].view(1, 1, -1, 1)
+        ref = torch.nn.functional.interpolate(src, size=(n, 1), mode="bilinear").view(-1)
+        assert (got[b] - ref).abs().max() <= 2e-6, b
+
+
+def test_lr_schedule_and_add_densification_stats():
+    f = topology.get_expon_lr_func(1.6e-4, 1.6e-6, lr_delay_mult=0.01, max_steps=30000)
+    assert f(0) == pytest.approx(1.6e-4) and f(30000) == pytest.approx(1.6e-6) and f(15000) == pytest.approx(1.6e-5)
+    assert f(-1) == 0.0 and topology.get_expon_lr_func(0.0, 0.0)(5) == 0.0
+    g = topology.get_expon_lr_func(1e-2, 1e-4, lr_delay_steps=100, lr_delay_mult=0.1, max_steps=1000)
+    assert g(0) == pytest.approx(1e-3) and g(100) == pytest.approx(1e-2 * 10 ** (-0.2))
+    cp, width, opl, isb = synth.random_curves(5, seed=1)
+    m = CpuModel(0, n_gaussians=4, device="cpu").create_from_curves(cp, width, opl, isb)
+    m.training_setup(Args())
+    assert m.update_learning_rate(0) == pytest.approx(1.6e-4)
+    vs = torch.zeros(20, 3, requires_grad=True)
+    vs.grad = torch.arange(60.0).view(20, 3)
+    keep = torch.arange(20) % 2 == 0
+    m.add_densification_stats(vs, keep)
+    assert torch.equal(m.denom.view(-1), keep.float())
+    assert m.xyz_gradient_accum[2, 0] == pytest.approx((6.0 ** 2 + 7.0 ** 2) ** 0.5)
+
+
+def test_checkpoint_round_trip_keeps_curves_and_moments(tmp_path):
+    d = load("densify")
+    m = model_from(d)
+    blob = m.capture()
+    assert len(blob) == 13 and blob[0] == 0
+    torch.save(blob, tmp_path / "chkpnt.pth")
+    m2 = CpuModel(0, n_gaussians=m.n_gaussians, device="cpu")
+    m2.restore(torch.load(tmp_path / "chkpnt.pth", weights_only=False), Args())
+    for a in ("_curve_points", "_width", "_opacity", "_mask", "_xyz", "_rotation", "_scaling"):
+        assert torch.equal(getattr(m, a).detach(), getattr(m2, a).detach()), a
+    assert torch.equal(m.is_bezier, m2.is_bezier) and torch.equal(m.denom, m2.denom)
+    for g1, g2 in zip(m.optimizer.param_groups, m2.optimizer.param_groups):
+        s1, s2 = m.optimizer.state[g1["params"][0]], m2.optimizer.state[g2["params"][0]]
+        assert torch.equal(s1["exp_avg"], s2["exp_avg"]) and torch.equal(s1["exp_avg_sq"], s2["exp_avg_sq"])
+    with pytest.raises(ValueError):
+        m2.restore(blob[:12], Args())          # the reference's tuple: no curve parameters in it
+    m.save_curves(tmp_path / "curves.pt")
+    m3 = CpuModel(0, n_gaussians=m.n_gaussians, device="cpu").load_curves(tmp_path / "curves.pt")
+    assert torch.equal(m3._curve_points.detach(), m._curve_points.detach()) and torch.equal(m3.is_bezier, m.is_bezier)
+
+
+def test_ply_and_parametric_edges_files(tmp_path):
+    cp, width, opl, isb = synth.random_curves(9, seed=4, line_fraction=0.4)
+    m = CpuModel(0, n_gaussians=6, device="cpu").create_from_curves(cp, width, opl, isb)
+    m.save_ply(str(tmp_path / "point_cloud" / "iteration_7" / "point_cloud.ply"))
+    got = curve_io.read_ply(str(tmp_path / "point_cloud" / "iteration_7" / "point_cloud.ply"))
+    assert list(got) == ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "opacity", "scale_0", "scale_1", "scale_2",
+                         "rot_0", "rot_1", "rot_2", "rot_3"]
+    assert np.array_equal(np.stack([got["x"], got["y"], got["z"]], 1), m._xyz.detach().numpy())
+    assert np.array_equal(np.stack([got[f"rot_{i}"] for i in range(4)], 1), m._rotation.detach().numpy())
+    assert np.allclose(got["opacity"], m._opacity.detach().repeat_interleave(6).numpy(), atol=1e-6)
+
+    pts, d = curve_io.extract_curves(m, str(tmp_path))
+    on_disk = json.load(open(tmp_path / "parametric_edges.json"))
+    assert on_disk == d
+    nb, nl = int(isb.sum()), int((~isb).sum())
+    assert np.asarray(d["curves_ctl_pts"]).shape == (nb, 4, 3) and np.asarray(d["lines_end_pts"]).shape == (nl, 6)
+    assert np.allclose(np.asarray(d["curves_ctl_pts"]), cp[isb].numpy())
+    assert np.allclose(np.asarray(d["lines_end_pts"]).reshape(-1, 2, 3), cp[~isb][:, [0, 3]].numpy())
+    back = curve_io.read_ply(str(tmp_path / "edge_points.ply"))
+    assert np.allclose(np.stack([back["x"], back["y"], back["z"]], 1), pts, atol=1e-6) and len(pts) > 50
+    # Simpson arc length: exact for a straight cubic, and close to a fine polyline for a bent one
+    straight = np.stack([np.linspace([0, 0, 0], [3.0, 4.0, 0.0], 4)])
+    assert curve_io.bezier_lengths(straight)[0] == pytest.approx(5.0, abs=1e-9)
+    c = cp[isb][:3].double().numpy()
+    t = np.linspace(0, 1, 20001)[:, None, None]
+    poly = (1 - t) ** 3 * c[:, 0] + 3 * (1 - t) ** 2 * t * c[:, 1] + 3 * (1 - t) * t ** 2 * c[:, 2] + t ** 3 * c[:, 3]
+    fine = np.linalg.norm(np.diff(poly, axis=0), axis=-1).sum(0)
+    assert np.allclose(curve_io.bezier_lengths(c), fine, rtol=1e-6)
