@@ -119,13 +119,13 @@ class CurveTopology:
         self.denom = torch.zeros((P, 1), device=dev)
         self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
         g = lambda k, d=0.0: getattr(training_args, k, d)
-        rates = {"f_dc": g("feature_lr", 0.0025), "f_rest": g("feature_lr", 0.0025) / 20.0, "opacity": g("opacity_lr", 0.05),
-                 "width": g("scaling_lr", 0.005), "curve_points": g("lr_curve_points_init", 0.00016),
+        rates = {"f_dc": g("feature_lr", 0.0025), "f_rest": g("feature_lr", 0.0025) / 20.0, "opacity": g("opacity_lr", 0.025),
+                 "width": g("scaling_lr", 0.005), "curve_points": g("lr_curve_points_init", 0.0005),
                  "mask": g("mask_lr", 0.01)}
         groups = [{"params": [getattr(self, attr)], "lr": rates[name], "name": name} for name, attr in self._GROUPS]
         self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
         self.curve_scheduler_args = get_expon_lr_func(
-            lr_init=g("lr_curve_points_init", 0.00016), lr_final=g("lr_curve_points_final", 0.0000016),
+            lr_init=g("lr_curve_points_init", 0.0005), lr_final=g("lr_curve_points_final", 0.000005),
             lr_delay_mult=g("position_lr_delay_mult", 0.01), max_steps=g("position_lr_max_steps", 30000))
         return self.optimizer
 
@@ -153,6 +153,12 @@ class CurveTopology:
     def add_densification_stats(self, viewspace_point_tensor, update_filter):
         """scene/gaussian_model.py:618-620 (update_filter: boolean (P,) or index tensor)."""
         g = viewspace_point_tensor.grad
+        if update_filter.dtype == torch.bool:
+            # masked adds: same sums as the reference's boolean indexing without its host-synchronising nonzero()
+            f = update_filter.view(-1, 1).to(self.denom.dtype)
+            self.xyz_gradient_accum += torch.norm(g[:, :2], dim=-1, keepdim=True) * f
+            self.denom += f
+            return
         self.xyz_gradient_accum[update_filter] += torch.norm(g[update_filter, :2], dim=-1, keepdim=True)
         self.denom[update_filter] += 1
 

@@ -1,0 +1,165 @@
+"""One training iteration as the reference's train.py runs it (train.py:75-243), on the B200-native ops.
+
+The caller of the hot path: learning-rate update -> render one view -> image loss + curve regularisers ->
+backward -> densification statistics / periodic curve-set surgery -> Adam step -> re-sample. Differences
+from the reference loop are host-side only:
+  * the image loss, curve smoothness and endpoint connectivity are the fused ops (loss.py, regularizers.py);
+  * nothing reads a device scalar per iteration (the reference's five `.item()` calls for its progress bar,
+    train.py:153-157, and the `visibility_filter.sum() > 0` tests, :114/:119); `stats()` reads them on demand;
+  * RANSAC curve merging / line fitting (train.py:213-215) is not run (topology.py).
+"""
+from __future__ import annotations
+
+import random
+from typing import Optional, Sequence
+
+import torch
+
+from .loss import edge_ssim_loss
+from .regularizers import curve_smoothness, endpoint_connectivity
+from .renderer import render
+
+
+class OptimizationParams:
+    """Defaults of arguments/__init__.py:78-124 (the fields this loop reads)."""
+    iterations = 10_000
+    position_lr_delay_mult = 0.01
+    position_lr_max_steps = 30_000
+    lr_curve_points_init = 0.0005
+    lr_curve_points_final = 0.000005
+    feature_lr = 0.0025
+    opacity_lr = 0.025
+    scaling_lr = 0.005
+    mask_lr = 0.01
+    lambda_dssim = 0.1
+    opacity_cull = 0.01
+    opacity_cull_second = 0.05
+    opacity_loss_weight = 0.01
+    lambda_mse = 10.0
+    lambda_curve_smo = 0.1
+    lambda_points_conn = 0.1
+    lambda_width = 0.01
+    lambda_mask = 0.0005
+    mask_threshold = 0.01
+    densification_interval = 2000
+    opacity_reset_interval = 3000
+    densify_from_iter = 500
+    densify_until_iter = 7000
+    conn_from_iter = 7000
+    densify_grad_threshold = 2000
+    threshold_angle = 20
+    threshold_angle_skip = 30
+
+    def __init__(self, **overrides):
+        for k, v in overrides.items():
+            if not hasattr(type(self), k):
+                raise AttributeError(f"unknown optimization parameter {k}")
+            setattr(self, k, v)
+
+
+class PipelineParams:
+    debug = False
+    antialiasing = False
+    render_geo = True
+
+
+class TrainLoop:
+    """`TrainLoop(model, cameras, targets, opt).step()` = one iteration of train.py's loop body.
+
+    cameras: objects with the reference Camera attributes; targets: the per-view edge maps (1,H,W) on the device
+    (train.py:99 `original_image[:1]`). `model.training_setup(opt)` is called here.
+    """
+
+    def __init__(self, model, cameras: Sequence, targets: Sequence[torch.Tensor], opt: Optional[OptimizationParams] = None,
+                 pipe=None, background: Optional[torch.Tensor] = None, cameras_extent: float = 1.0, seed: int = 0):
+        self.model, self.cameras, self.targets = model, list(cameras), list(targets)
+        self.opt = opt or OptimizationParams()
+        self.pipe = pipe or PipelineParams()
+        dev = model._curve_points.device
+        self.bg = background if background is not None else torch.zeros(3, device=dev)
+        self.cameras_extent = cameras_extent
+        self.iteration = 0
+        self.rng = random.Random(seed)
+        self._stack: list = []
+        model.training_setup(self.opt)
+        self.last = {}
+
+    def _next_view(self) -> int:
+        if not self._stack:
+            self._stack = list(range(len(self.cameras)))
+        return self._stack.pop(self.rng.randint(0, len(self._stack) - 1))
+
+    def loss_terms(self, pkg, gt, iteration):
+        """The scalar of train.py:101-146 as device tensors: (total, {name: term})."""
+        opt, m = self.opt, self.model
+        terms = {"image": edge_ssim_loss(pkg["render_raw"], gt, threshold=0.1, lambda_mse=opt.lambda_mse,
+                                         lambda_dssim=opt.lambda_dssim, clamp=True)}
+        if iteration >= opt.densify_until_iter:
+            terms["mask"] = opt.lambda_mask * torch.sigmoid(m._mask).mean()
+        # opacity regulariser over the visible Gaussians (train.py:114-117); a masked mean instead of the
+        # reference's host-synchronising boolean indexing, same value
+        vis = (pkg["radii"] > 0).view(-1, 1).float()
+        opa = torch.log(1 + m.get_opacity ** 2 / 0.5)
+        terms["opacity"] = opt.opacity_loss_weight * (opa * vis).sum() / vis.sum().clamp_min(1.0)
+        if opt.lambda_curve_smo > 0:
+            terms["curve_smo"] = opt.lambda_curve_smo * curve_smoothness(m._rotation, m.n_gaussians)
+        if opt.lambda_width > 0:
+            w = m.get_curve_width
+            over = (w >= 0.005).float()
+            terms["width"] = opt.lambda_width * ((w - 0.005) * over).sum() / over.sum().clamp_min(1.0)
+        if opt.lambda_points_conn > 0 and iteration > opt.conn_from_iter:
+            terms["curve_conn"] = opt.lambda_points_conn * endpoint_connectivity(m.get_curve_points, 0.05)
+        total = terms["image"]
+        for k, v in terms.items():
+            if k != "image":
+                total = total + v
+        return total, terms
+
+    def step(self):
+        opt, m = self.opt, self.model
+        self.iteration += 1
+        it = self.iteration
+        m.update_learning_rate(it)
+        v = self._next_view()
+        cam, gt = self.cameras[v], self.targets[v]
+        pkg = render(cam, m, self.pipe, self.bg, use_mask=it >= opt.densify_until_iter, mask_thr=opt.mask_threshold)
+        loss, terms = self.loss_terms(pkg, gt, it)
+        loss.backward()
+        self.last = {"loss": loss.detach(), **{k: t.detach() for k, t in terms.items()}}
+        with torch.no_grad():
+            radii = pkg["radii"]
+            if it < opt.densify_until_iter:
+                visible = radii > 0
+                m.max_radii2D = torch.where(visible, torch.maximum(m.max_radii2D, radii.to(m.max_radii2D.dtype)), m.max_radii2D)
+                m.add_densification_stats(pkg["viewspace_points"], visible)
+                if it > opt.densify_from_iter and it % opt.densification_interval == 0:
+                    size_threshold = 20 if it > opt.opacity_reset_interval else None
+                    self._surgery(lambda: m.densify_and_prune(opt.densify_grad_threshold, opt.opacity_cull,
+                                                              self.cameras_extent, size_threshold, radii))
+            if it == opt.densify_until_iter:
+                def second_cull():
+                    m.prune_curves((m.get_curve_opacity <= opt.opacity_cull_second).reshape(-1))
+                    m.fix_opacity()
+                self._surgery(second_cull)
+            if it % 1000 == 500 and it > opt.densify_until_iter:
+                def prune_trim():
+                    m.only_prune(opt.opacity_cull, opt.mask_threshold)
+                    m.mask_trim_split(opt.mask_threshold)
+                self._surgery(prune_trim)
+            if it % 1000 == 0 and it > 3000 and it != opt.iterations:
+                self._surgery(lambda: m.curve_split_curvature(opt.threshold_angle, opt.threshold_angle_skip))
+            if it < opt.iterations:
+                m.optimizer.step()
+                m.optimizer.zero_grad(set_to_none=True)
+        m.prepare_scaling_rot()
+        return loss
+
+    def _surgery(self, fn):
+        """Curve-set edits replace the parameters: their pending gradients go with the old tensors, exactly as in
+        the reference (the Adam step that follows sees .grad = None for the new tensors and skips them)."""
+        fn()
+
+    def stats(self) -> dict:
+        """Host copies of the last iteration's loss terms (one synchronisation, on demand)."""
+        return {k: float(v) for k, v in self.last.items()} | {"curves": int(self.model._curve_points.shape[0]),
+                                                             "iteration": self.iteration}
