@@ -58,12 +58,11 @@ def test_scheduled_surgery_runs_between_steps(cuda_dev):
     assert not model._opacity.requires_grad              # fix_opacity at densify_until_iter
     # jump to the late-schedule events without running thousands of steps
     loop.iteration = 1498
-    loop.step(); loop.step()                             # 1500: only_prune + mask_trim_split
-    loop.iteration = 3999
-    before = model._curve_points.shape[0]
-    loop.iteration = 3999 if opt.iterations > 4000 else 2999
+    loop.step()
+    loop.step()                                          # 1500: only_prune + mask_trim_split
     opt.iterations = 10_000
     loop.iteration = 3999
+    before = model._curve_points.shape[0]
     loop.step()                                          # 4000: curve_split_curvature (thresholds of 1-2 degrees)
     assert model._curve_points.shape[0] >= before
     B, n = model._curve_points.shape[0], model.n_gaussians
