@@ -262,15 +262,11 @@ rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_
   keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
 }
 
-// Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry.
-__global__ void __launch_bounds__(256)
-gather_records(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __restrict__ sorted_tiles,
-               const uint32_t* __restrict__ sorted_vals, GeomState g, const float* __restrict__ colors,
-               const float* __restrict__ all_map, uint2* __restrict__ ranges, Rec* __restrict__ rec,
-               uint32_t* __restrict__ point_list) {
-  pdl_wait();
-  if (d_n) R = min(R, int64_t(*d_n));   // capacity mode: the count lives on the device
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+// One sorted instance: tile range boundaries, point list entry, and its 48-byte record into the CTA's staging area.
+__device__ __forceinline__ void
+gather_one(int64_t i, int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint32_t* __restrict__ sorted_vals,
+           const GeomState& g, const float* __restrict__ colors, const float* __restrict__ all_map,
+           uint2* __restrict__ ranges, uint32_t* __restrict__ point_list, float4* s_out) {
   if (i >= R) return;
   {
     // per-tile [start, end) into the sorted list (rasterizer_impl.cu:116-138); ranges is zero-filled
@@ -288,10 +284,30 @@ gather_records(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __re
   const float4 co = g.conic_o[id];
   float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
   if (all_map) mp = __ldg(reinterpret_cast<const float4*>(all_map) + id);
-  float4* out = reinterpret_cast<float4*>(rec + i);
-  out[0] = make_float4(xy.x, xy.y, co.x, co.y);
-  out[1] = make_float4(co.z, co.w, __ldg(colors + id), 1.f / g.depth[id]);
-  out[2] = mp;
+  // the CTA's 256 records are one contiguous 12 KB span: stage them in shared memory (16-byte words at stride 3:
+  // conflict-free) and write the span with consecutive 128-bit stores instead of 48-byte-strided ones
+  s_out[threadIdx.x * 3 + 0] = make_float4(xy.x, xy.y, co.x, co.y);
+  s_out[threadIdx.x * 3 + 1] = make_float4(co.z, co.w, __ldg(colors + id), 1.f / g.depth[id]);
+  s_out[threadIdx.x * 3 + 2] = mp;
+}
+
+// Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry.
+__global__ void __launch_bounds__(256)
+gather_records(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __restrict__ sorted_tiles,
+               const uint32_t* __restrict__ sorted_vals, GeomState g, const float* __restrict__ colors,
+               const float* __restrict__ all_map, uint2* __restrict__ ranges, Rec* __restrict__ rec,
+               uint32_t* __restrict__ point_list) {
+  pdl_wait();
+  __shared__ float4 s_out[256 * 3];
+  if (d_n) R = min(R, int64_t(*d_n));   // capacity mode: the count lives on the device
+  const int64_t blk0 = int64_t(blockIdx.x) * 256;
+  if (blk0 >= R) return;
+  const int64_t i = blk0 + threadIdx.x;
+  gather_one(i, R, sorted_tiles, sorted_vals, g, colors, all_map, ranges, point_list, s_out);
+  __syncthreads();
+  const int nvec = int(min(int64_t(256), R - blk0)) * 3;
+  float4* dst = reinterpret_cast<float4*>(rec + blk0);
+  for (int k = threadIdx.x; k < nvec; k += 256) dst[k] = s_out[k];
 }
 
 // ---------------------------------------------------------------------------
