@@ -395,8 +395,11 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* _
 // cp.async.bulk while all threads blend the previous batch. Each warp first tests 32 records
 // at a time (one per lane, block_candidate in common.cuh) against its pixel block and only
 // walks the instances that can reach it, in list order (forward.cu:331-396 semantics).
+#ifndef CG_FWD_CTAS
+#define CG_FWD_CTAS 6
+#endif
 template <bool GEO>
-__global__ void __launch_bounds__(BLEND_THREADS, 2048 / BLEND_THREADS * 3 / 4)
+__global__ void __launch_bounds__(BLEND_THREADS, CG_FWD_CTAS * (256 / BLEND_THREADS))
 blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int grid_x,
           const Rec* __restrict__ rec, int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,

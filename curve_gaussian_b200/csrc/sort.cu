@@ -80,8 +80,11 @@ struct SortSmem {
   uint32_t tile_id;
 };
 
+#ifndef CG_SORT_CTAS
+#define CG_SORT_CTAS 3
+#endif
 template <typename K>
-__global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 4 ? CG_SORT_CTAS : 2)
 sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                    int64_t R, const uint32_t* __restrict__ d_n, int shift, uint32_t dmask,

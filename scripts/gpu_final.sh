@@ -13,7 +13,28 @@ timeout -k 10 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smok
 timeout -k 10 300 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 timeout -k 10 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "ref arm exit $?"
 timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches.csv \
-  python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
-timeout -k 10 700 ncu --set full --clock-control none --import-source on -k regex:"^(activate_|blend_|emit_keys|gather_records|init_depth_keys|perm_block_sums|preprocess_fwd|preprocess_bwd|sample_|scan_block_sums|sort_|ssim_)" -s 200 -c 40 -o $OUT/full \
-  python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
+  python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline --no-small-scene > $OUT/ncu_launch_bench.log 2>&1
+# one --set full pass over the kernels that make up >90 % of the step (FULL=1: every libcurvegs kernel of one step)
+if [ "${FULL:-0}" = "1" ]; then
+  KRE='^(activate_|blend_|emit_keys|gather_records|init_depth_keys|perm_block_sums|preprocess_fwd|preprocess_bwd|sample_|scan_block_sums|sort_|ssim_)'; SKIP=200; CNT=40
+else
+  KRE='^(blend_|gather_records|sort_onesweep|preprocess_bwd|sample_bwd_point|ssim_fwd|emit_keys)'; SKIP=60; CNT=14
+fi
+timeout -k 10 500 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s $SKIP -c $CNT -o $OUT/full \
+  python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline --no-small-scene > $OUT/ncu_full_bench.log 2>&1
 ls -la $OUT
+# A/B of kernel variants built by `python -m curve_gaussian_b200.build --variant ...` (dev only; last, so that
+# running out of time here costs nothing above)
+for f in curve_gaussian_b200/variants/libcurvegs_*.so; do
+  [ -e "$f" ] || continue
+  n=$(basename $f .so); n=${n#libcurvegs_}
+  CURVEGS_LIB=$PWD/$f timeout -k 10 120 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-small-scene > $OUT/bench_variant_$n.json 2> $OUT/bench_variant_$n.err
+  python - "$OUT/bench_variant_$n.json" "$n" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("variant", sys.argv[2], d["value"], d["ms_per_step"], d["e2e"]["value"], d["stage_ms"])
+except Exception as e:
+    print("variant", sys.argv[2], "FAILED", e)
+PY
+done
