@@ -136,6 +136,9 @@ class CurveTopology:
                 return group["lr"]
 
     def _adopt(self, tensors: Dict[str, nn.Parameter]) -> None:
+        # every replacement of a parameter tensor bumps the version: anything that captured the old tensors
+        # (a CUDA graph of the step, trainer.TrainLoop) knows it has to be rebuilt
+        self.topology_version = getattr(self, "topology_version", 0) + 1
         for name, attr in self._GROUPS:
             if name in tensors:
                 setattr(self, attr, tensors[name])

@@ -15,7 +15,10 @@ from typing import Optional, Sequence
 
 import torch
 
+from . import rasterizer as _rz
+from .graph import GraphedStep, StaticCamera
 from .loss import edge_ssim_loss
+from .parallel import FlatGrad
 from .regularizers import curve_smoothness, endpoint_connectivity
 from .renderer import render
 
@@ -71,7 +74,8 @@ class TrainLoop:
     """
 
     def __init__(self, model, cameras: Sequence, targets: Sequence[torch.Tensor], opt: Optional[OptimizationParams] = None,
-                 pipe=None, background: Optional[torch.Tensor] = None, cameras_extent: float = 1.0, seed: int = 0):
+                 pipe=None, background: Optional[torch.Tensor] = None, cameras_extent: float = 1.0, seed: int = 0,
+                 graph: bool = False):
         self.model, self.cameras, self.targets = model, list(cameras), list(targets)
         self.opt = opt or OptimizationParams()
         self.pipe = pipe or PipelineParams()
@@ -83,6 +87,15 @@ class TrainLoop:
         self._stack: list = []
         model.training_setup(self.opt)
         self.last = {}
+        # graph=True: render -> loss -> backward is replayed from a CUDA graph (graph.GraphedStep) and re-captured
+        # whenever the curve set or the set of active loss terms changes; all views must share size and FoV
+        self.graph = bool(graph)
+        self.captures = 0
+        self._gs = self._sig = self._fg = None
+        if self.graph:
+            self._policy = _rz.CapacityBinning()
+            self._scam = StaticCamera(self.cameras[0])
+            self._gt = torch.empty_like(self.targets[0])
 
     def _next_view(self) -> int:
         if not self._stack:
@@ -122,10 +135,15 @@ class TrainLoop:
         m.update_learning_rate(it)
         v = self._next_view()
         cam, gt = self.cameras[v], self.targets[v]
-        pkg = render(cam, m, self.pipe, self.bg, use_mask=it >= opt.densify_until_iter, mask_thr=opt.mask_threshold)
-        loss, terms = self.loss_terms(pkg, gt, it)
-        loss.backward()
+        if self.graph:
+            loss, terms, pkg = self._graph_forward_backward(cam, gt, it)
+        else:
+            pkg = render(cam, m, self.pipe, self.bg, use_mask=it >= opt.densify_until_iter, mask_thr=opt.mask_threshold)
+            loss, terms = self.loss_terms(pkg, gt, it)
+            loss.backward()
         self.last = {"loss": loss.detach(), **{k: t.detach() for k, t in terms.items()}}
+        # curve-set edits below replace the parameters: their pending gradients go with the old tensors, exactly as
+        # in the reference (the Adam step that follows sees .grad = None for the new tensors and skips them)
         with torch.no_grad():
             radii = pkg["radii"]
             if it < opt.densify_until_iter:
@@ -134,30 +152,75 @@ class TrainLoop:
                 m.add_densification_stats(pkg["viewspace_points"], visible)
                 if it > opt.densify_from_iter and it % opt.densification_interval == 0:
                     size_threshold = 20 if it > opt.opacity_reset_interval else None
-                    self._surgery(lambda: m.densify_and_prune(opt.densify_grad_threshold, opt.opacity_cull,
-                                                              self.cameras_extent, size_threshold, radii))
+                    m.densify_and_prune(opt.densify_grad_threshold, opt.opacity_cull, self.cameras_extent,
+                                        size_threshold, radii)
             if it == opt.densify_until_iter:
-                def second_cull():
-                    m.prune_curves((m.get_curve_opacity <= opt.opacity_cull_second).reshape(-1))
-                    m.fix_opacity()
-                self._surgery(second_cull)
+                m.prune_curves((m.get_curve_opacity <= opt.opacity_cull_second).reshape(-1))
+                m.fix_opacity()
             if it % 1000 == 500 and it > opt.densify_until_iter:
-                def prune_trim():
-                    m.only_prune(opt.opacity_cull, opt.mask_threshold)
-                    m.mask_trim_split(opt.mask_threshold)
-                self._surgery(prune_trim)
+                m.only_prune(opt.opacity_cull, opt.mask_threshold)
+                m.mask_trim_split(opt.mask_threshold)
             if it % 1000 == 0 and it > 3000 and it != opt.iterations:
-                self._surgery(lambda: m.curve_split_curvature(opt.threshold_angle, opt.threshold_angle_skip))
+                m.curve_split_curvature(opt.threshold_angle, opt.threshold_angle_skip)
             if it < opt.iterations:
                 m.optimizer.step()
-                m.optimizer.zero_grad(set_to_none=True)
-        m.prepare_scaling_rot()
+                if not self.graph:      # (the captured step zeroes its flat gradient buffer itself)
+                    m.optimizer.zero_grad(set_to_none=True)
+        if not self.graph or self._signature(it + 1) != self._sig:
+            m.prepare_scaling_rot()     # (a captured step re-samples at its start)
         return loss
 
-    def _surgery(self, fn):
-        """Curve-set edits replace the parameters: their pending gradients go with the old tensors, exactly as in
-        the reference (the Adam step that follows sees .grad = None for the new tensors and skips them)."""
-        fn()
+    # ---- CUDA-graph mode -------------------------------------------------------------------------------------
+    def _trainable(self):
+        m = self.model
+        return [p for p in (m._curve_points, m._width, m._opacity, m._mask) if p.requires_grad]
+
+    def _signature(self, it):
+        opt = self.opt
+        m = self.model
+        return (getattr(m, "topology_version", 0), tuple(p.requires_grad for p in (m._curve_points, m._width, m._opacity, m._mask)),
+                it >= opt.densify_until_iter, opt.lambda_points_conn > 0 and it > opt.conn_from_iter)
+
+    def _graph_forward_backward(self, cam, gt, it):
+        m, opt = self.model, self.opt
+        sig = self._signature(it)
+        if sig != self._sig:
+            use_mask = it >= opt.densify_until_iter
+
+            def body():
+                m.prepare_scaling_rot()
+                pkg = render(self._scam, m, self.pipe, self.bg, use_mask=use_mask, mask_thr=opt.mask_threshold)
+                loss, terms = self.loss_terms(pkg, self._gt, it)
+                loss.backward()
+                return loss, terms, pkg
+
+            # which tensors autograd reaches with this set of loss terms: only those get a slot in the flat gradient
+            # buffer, so Adam skips the others exactly as it does in the eager loop (their .grad stays None)
+            params = self._trainable()
+            for p in (m._curve_points, m._width, m._opacity, m._mask, m._features_dc, m._features_rest):
+                p.grad = None
+            self._scam.load(cam)
+            self._gt.copy_(gt)
+            body()
+            reached = [p for p in params if p.grad is not None]
+            self._fg = FlatGrad(reached)
+
+            def fn():
+                self._fg.zero()
+                return body()
+
+            loads = [(lambda c=c, t=t: (self._scam.load(c), self._gt.copy_(t))) for c, t in zip(self.cameras, self.targets)]
+            self._gs = GraphedStep(fn, policy=self._policy, calibrate=loads).capture()
+            self._sig = sig
+            self.captures += 1
+        self._scam.load(cam)
+        self._gt.copy_(gt, non_blocking=True)
+        return self._gs.replay()
+
+    def verify(self) -> bool:
+        """Graph mode, after a synchronisation: False if recent replays overflowed the captured binning capacity
+        (those iterations used truncated instance lists); the step has been re-captured with a larger one."""
+        return True if self._gs is None else self._gs.verify()
 
     def stats(self) -> dict:
         """Host copies of the last iteration's loss terms (one synchronisation, on demand)."""

@@ -76,3 +76,28 @@ def test_scheduled_surgery_runs_between_steps(cuda_dev):
     s = loop.stats()
     assert s["curves"] == B and all(v == v for v in s.values())    # no NaN
     assert "curve_conn" in s and "mask" in s
+
+
+def test_graph_mode_follows_the_eager_loop(cuda_dev):
+    """Same scene, same view order: the loop that replays render -> loss -> backward from a CUDA graph (re-captured
+    when densification replaces the parameters) tracks the eager loop; differences come from fp32 atomics only."""
+    runs = []
+    for graph in (False, True):
+        model, cams, gts = make_scene(cuda_dev, B=50, views=4)
+        opt = OptimizationParams(iterations=1000, densify_from_iter=3, densification_interval=8, densify_until_iter=20,
+                                 densify_grad_threshold=5e-5, conn_from_iter=12, lr_curve_points_init=1e-3)
+        loop = TrainLoop(model, cams, gts, opt, seed=5, graph=graph)
+        losses, counts = [], []
+        for _ in range(30):
+            loop.step()
+            losses.append(loop.stats()["loss"])
+            counts.append(model._curve_points.shape[0])
+        torch.cuda.synchronize()
+        assert loop.verify()
+        runs.append((losses, counts, model._curve_points.detach().clone(), loop))
+    (l0, c0, p0, _), (l1, c1, p1, g) = runs
+    assert c0 == c1 and max(c0) > c0[0]                      # the same splits / prunes happened
+    assert g.captures >= 3                                   # start, after a split, after fix_opacity / new loss terms
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * abs(a), (l0, l1)
+    assert ((p0 - p1).abs().max() / p0.abs().max()).item() < 1e-3
