@@ -186,6 +186,7 @@ class TrainLoop:
         sig = self._signature(it)
         if sig != self._sig:
             use_mask = it >= opt.densify_until_iter
+            self._gs = None   # the old capture's outputs keep its autograd graph (and that graph's streams) alive
 
             def body():
                 m.prepare_scaling_rot()

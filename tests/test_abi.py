@@ -57,6 +57,19 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert b"image size" in lib.cg_last_error()
 
 
+def test_capacity_forward_rejects_bad_arguments_before_touching_the_gpu():
+    lib = _lib.load()
+    import ctypes as C
+    s = _lib.RasterSettings()
+    s.image_width, s.image_height = 64, 48
+    s.bg = s.viewmatrix = s.projmatrix = 0x1000          # never dereferenced: argument checks come first
+    args = [None] * 9 + [0] + [None] * 8
+    assert lib.cg_raster_fwd_capacity(C.byref(s), 0, 100, *args) == -1 and b"P" in lib.cg_last_error()
+    assert lib.cg_raster_fwd_capacity(C.byref(s), 10, 0, *args) == -1 and b"R_cap" in lib.cg_last_error()
+    assert lib.cg_raster_fwd_capacity(C.byref(s), 10, 1 << 30, *args) == -1
+    assert lib.cg_raster_fwd_capacity(C.byref(s), 10, 100, *args) == -1 and b"means3D" in lib.cg_last_error()
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "curve_gaussian_b200")
     for dirpath, _, files in os.walk(pkg):
