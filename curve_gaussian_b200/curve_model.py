@@ -2,7 +2,7 @@
 names, properties and `prepare_scaling_rot()`, with the sampling math running as the fused CUDA op in
 sampling.py (:54-198, the hot path). The training-time surgery on the curve set and the optimizer
 bookkeeping (:200-459) come from topology.CurveTopology; checkpoints and the on-disk formats (ply,
-parametric_edges.json) from curve_io. RANSAC curve merging (:462-640) and the mesh/point-cloud debug dumps
+parametric_edges.json) from curve_io. RANSAC curve merging (:462-588) and the mesh/point-cloud debug dumps
 (:643-727) are not carried over.
 """
 from __future__ import annotations

@@ -6,8 +6,8 @@ rearrange the per-curve tensors `_curve_points/_width/_opacity/_mask/is_bezier` 
 runs as a handful of whole-tensor device ops, no per-curve host loop, and ends with `prepare_scaling_rot()` so
 the hot path sees the new curve set. Method names, arguments and results follow the reference.
 
-Not carried over: `merge_curves` / `fit_curve_to_line` (RANSAC line fits through skimage + the repo's
-edge_extraction package on the host) - a different subsystem, see DESIGN.md.
+Not carried over: `merge_curves` (RANSAC + least-squares Bezier refits through skimage / scipy and the
+reference's edge_extraction package on the host) - a different subsystem, see DESIGN.md.
 """
 from __future__ import annotations
 
@@ -272,3 +272,28 @@ class CurveTopology:
         self._adopt(self.replace_tensor_to_optimizer(new_mask.view(-1, n, 1).contiguous(), "mask"))
         self._adopt(self.replace_tensor_to_optimizer(trimmed.contiguous(), "curve_points"))
         self.prepare_scaling_rot()
+
+    def fit_curve_to_line(self, threshold=0.002, threshold_max=0.004, sample_num=100):
+        """Re-label as straight segments the Beziers whose sample_num points lie within `threshold` (mean) and
+        `threshold_max` (max) of their least-squares line (gaussian_curve_model.py:590-626 with
+        edge_extraction/fitting.py:74-97), for all curves at once: batched 3x3 eigen-decomposition instead of a
+        per-curve numpy loop. As in the reference the control points keep their values (its write of the fitted
+        end points goes to a temporary copy, :612-613), `is_bezier` flips and the Adam moments of the curve
+        points restart. Returns the number of curves re-labelled."""
+        cp = self._curve_points.detach()
+        t = torch.linspace(0, 1, sample_num, device=cp.device)[None, :, None]
+        p0, p1, p2, p3 = (cp[:, i][:, None, :] for i in range(4))
+        pts = (1 - t) ** 3 * p0 + 3 * (1 - t) ** 2 * t * p1 + 3 * (1 - t) * t ** 2 * p2 + t ** 3 * p3      # (B,S,3)
+        mean = pts.mean(dim=1, keepdim=True)
+        c = pts - mean
+        cov = c.transpose(1, 2) @ c / sample_num
+        direction = torch.linalg.eigh(cov).eigenvectors[..., -1]                 # largest eigenvalue
+        direction = direction / direction.norm(dim=-1, keepdim=True)
+        along = (c * direction[:, None, :]).sum(-1, keepdim=True)               # projections lie in [t_min, t_max]
+        dist = (c - along * direction[:, None, :]).norm(dim=-1)
+        straight = (dist.mean(dim=1) < threshold) & (dist.max(dim=1).values < threshold_max) & self.is_bezier
+        k = int(straight.sum())
+        if k:
+            self.is_bezier = self.is_bezier & ~straight
+            self._adopt(self.replace_tensor_to_optimizer(cp.clone(), "curve_points"))
+        return k

@@ -6,7 +6,7 @@ from the reference loop are host-side only:
   * the image loss, curve smoothness and endpoint connectivity are the fused ops (loss.py, regularizers.py);
   * nothing reads a device scalar per iteration (the reference's five `.item()` calls for its progress bar,
     train.py:153-157, and the `visibility_filter.sum() > 0` tests, :114/:119); `stats()` reads them on demand;
-  * RANSAC curve merging / line fitting (train.py:213-215) is not run (topology.py).
+  * RANSAC curve merging (`merge_curves`, train.py:215) is not run (topology.py).
 """
 from __future__ import annotations
 
@@ -50,6 +50,8 @@ class OptimizationParams:
     densify_until_iter = 7000
     conn_from_iter = 7000
     densify_grad_threshold = 2000
+    threshold_line = 0.0015
+    threshold_max_line = 0.005
     threshold_angle = 20
     threshold_angle_skip = 30
 
@@ -162,6 +164,8 @@ class TrainLoop:
                 m.mask_trim_split(opt.mask_threshold)
             if it % 1000 == 0 and it > 3000 and it != opt.iterations:
                 m.curve_split_curvature(opt.threshold_angle, opt.threshold_angle_skip)
+            if (it % 1000 == 0 and it > opt.densify_until_iter) or it == opt.iterations:
+                m.fit_curve_to_line(opt.threshold_line, opt.threshold_max_line)   # (merge_curves: not carried over)
             if it < opt.iterations:
                 m.optimizer.step()
                 if not self.graph:      # (the captured step zeroes its flat gradient buffer itself)

@@ -97,7 +97,7 @@ def state(m, prefix):
         if st is not None and group["name"] in ("curve_points", "width", "opacity", "mask"):
             out[prefix + "exp_avg_" + group["name"]] = st["exp_avg"]
             out[prefix + "exp_avg_sq_" + group["name"]] = st["exp_avg_sq"]
-    return {k: v.detach().cpu().numpy() for k, v in out.items()}
+    return {k: v.detach().cpu().numpy().copy() for k, v in out.items()}   # copy: some methods edit in place
 
 
 def main():
@@ -127,6 +127,21 @@ def main():
         "reset_opacity": lambda m, g: m.reset_opacity(),
         "fix_opacity": lambda m, g: m.fix_opacity(),
     }
+    # 3. fit_curve_to_line: nearly straight Beziers become lines (decision + unchanged points + reset moments)
+    m, g = build(GaussianCurveModel, 60, 12, seed=33, line_fraction=0.2)
+    with torch.no_grad():
+        cp = m._curve_points
+        chord = cp[:, 3] - cp[:, 0]
+        flat = torch.stack([cp[:, 0], cp[:, 0] + chord / 3, cp[:, 0] + 2 * chord / 3, cp[:, 3]], dim=1)
+        bend = torch.linspace(0, 1, 60)[:, None, None] ** 2          # from exactly straight to the original shape
+        cp.copy_(flat + bend * (cp - flat))
+    before = state(m, "in_")
+    with torch.no_grad():                       # train.py calls it inside its no_grad block (:166, :213-215)
+        m.fit_curve_to_line(0.002, 0.004)
+    after = state(m, "out_")
+    np.savez_compressed(os.path.join(HERE, "topology_fit_line.npz"), n=12, **before, **after)
+    print("fit_line", int(before["in_is_bezier"].sum()), "->", int(after["out_is_bezier"].sum()), "beziers")
+
     for name, fn in cases.items():
         m, g = build(GaussianCurveModel, 60, 12, seed=21, line_fraction=0.25)
         before = state(m, "in_")

@@ -205,3 +205,20 @@ def test_ply_and_parametric_edges_files(tmp_path):
     poly = (1 - t) ** 3 * c[:, 0] + 3 * (1 - t) ** 2 * t * c[:, 1] + 3 * (1 - t) * t ** 2 * c[:, 2] + t ** 3 * c[:, 3]
     fine = np.linalg.norm(np.diff(poly, axis=0), axis=-1).sum(0)
     assert np.allclose(curve_io.bezier_lengths(c), fine, rtol=1e-6)
+
+
+def test_fit_curve_to_line_matches_reference_decisions():
+    d = load("fit_line")
+    m = model_from(d)
+    before = m._curve_points.detach().clone()
+    k = m.fit_curve_to_line(0.002, 0.004)
+    want = torch.from_numpy(d["out_is_bezier"])
+    assert torch.equal(m.is_bezier, want)
+    assert k == int(torch.from_numpy(d["in_is_bezier"]).sum() - want.sum()) and k > 5
+    assert int(want.sum()) > 5                                                   # and some stayed curves
+    assert torch.equal(m._curve_points.detach(), before)                         # points untouched (reference :612-613)
+    assert torch.equal(m._curve_points.detach(), torch.from_numpy(d["out_curve_points"]))
+    st = [m.optimizer.state[g["params"][0]] for g in m.optimizer.param_groups if g["name"] == "curve_points"][0]
+    assert torch.equal(st["exp_avg"], torch.from_numpy(d["out_exp_avg_curve_points"]))   # moments restarted
+    assert float(st["exp_avg"].abs().max()) == 0.0
+    assert m.fit_curve_to_line(0.002, 0.004) == 0                                # idempotent
