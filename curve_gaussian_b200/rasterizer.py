@@ -129,6 +129,8 @@ class CapacityBinning:
             slot[2] = cap
             slot[:2].copy_(counter, non_blocking=True)
             return
+        if len(self._pending) >= 64:
+            self.poll()           # a caller that never polls: keep the queue bounded (may raise for an earlier step)
         slot = self._free.pop() if self._free else _pinned_i32(2)
         slot.copy_(counter, non_blocking=True)
         ev = torch.cuda.Event()
