@@ -10,21 +10,9 @@
 //   blend        forward.cu:279-417
 #include "common.cuh"
 #include "math.cuh"
+#include "stage.cuh"
 
 namespace cg {
-
-// ---------------------------------------------------------------------------
-// Stage `n` consecutive floats (n <= capacity of sm) with 128-bit loads.
-__device__ __forceinline__ void stage_floats(const float* __restrict__ src, float* sm, int n) {
-  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-    const int n4 = n >> 2;
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<float4*>(sm)[i] = __ldg(s4 + i);
-    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) sm[i] = __ldg(src + i);
-  } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = __ldg(src + i);
-  }
-}
 
 __device__ __forceinline__ float ndc_to_pix(float v, int S) {
   // double arithmetic on purpose: the reference's literals are doubles (auxiliary.h:40-43)
@@ -311,37 +299,6 @@ gather_records(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __re
 }
 
 // ---------------------------------------------------------------------------
-// mbarrier + 1-D bulk async copy (TMA) helpers.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
 constexpr int BATCH = BLEND_THREADS;
 
 // Launch order of the blend CTAs: tiles by descending list length (counting sort on the length quantised to
