@@ -45,3 +45,19 @@ def test_switch_nests_and_restores():
             assert rz._policy is b and b is not a
         assert rz._policy is a
     assert rz._policy is None
+
+
+def test_static_camera_takes_only_views_of_its_own_shape():
+    import torch
+    from curve_gaussian_b200 import synth
+    from curve_gaussian_b200.graph import StaticCamera
+    a, b = synth.random_cameras(2, 64, 48, seed=0)
+    other = synth.random_cameras(1, 80, 48, seed=0)[0]
+    sc = StaticCamera(a, device="cpu")
+    ptrs = (sc.world_view_transform.data_ptr(), sc.full_proj_transform.data_ptr(), sc.camera_center.data_ptr())
+    assert torch.equal(sc.world_view_transform, a.world_view_transform)
+    sc.load(b)
+    assert torch.equal(sc.full_proj_transform, b.full_proj_transform) and torch.equal(sc.camera_center, b.camera_center)
+    assert ptrs == (sc.world_view_transform.data_ptr(), sc.full_proj_transform.data_ptr(), sc.camera_center.data_ptr())
+    with pytest.raises(ValueError):
+        sc.load(other)
