@@ -87,6 +87,22 @@ class GaussianCurveModel(CurveTopology):
         self.prepare_scaling_rot()
         return self
 
+    def create_from_pcd(self, pcd, cam_infos, spatial_lr_scale: float, init_size: float = 0.5, n_control_points: int = 4):
+        """scene/gaussian_curve_model.py:142-178: one vertical Bezier per input point, sized by the distance to its
+        3 nearest neighbours; per-image exposure slots as the reference keeps them (`cam_infos`: objects with
+        `.image_name`, or an int count)."""
+        import numpy as np
+        assert n_control_points == 4
+        self.spatial_lr_scale = spatial_lr_scale
+        dev = self.sample_t.device
+        self.create_from_points(torch.as_tensor(np.asarray(pcd.points)).float(), init_size)
+        names = [getattr(c, "image_name", str(i)) for i, c in enumerate(cam_infos)] if not isinstance(cam_infos, int) \
+            else [str(i) for i in range(cam_infos)]
+        self.exposure_mapping = {name: i for i, name in enumerate(names)}
+        self.pretrained_exposures = None
+        self._exposure = nn.Parameter(torch.eye(3, 4, device=dev)[None].repeat(max(len(names), 1), 1, 1).requires_grad_(True))
+        return self
+
     def create_from_points(self, points, init_size=0.5):
         """The geometric part of create_from_pcd (scene/gaussian_curve_model.py:142-178)."""
         dev = self.sample_t.device
@@ -151,6 +167,41 @@ class GaussianCurveModel(CurveTopology):
 
     def parameters(self):
         return [self._curve_points, self._width, self._opacity, self._mask]
+
+    # ---- the remaining calls train.py makes on the model ---------------------
+    def oneupSHdegree(self):
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
+
+    def get_exposure_from_name(self, image_name):
+        if getattr(self, "pretrained_exposures", None) is None:
+            return self._exposure[self.exposure_mapping[image_name]]
+        return self.pretrained_exposures[image_name]
+
+    def merge_curves(self, *args, **kwargs):
+        """Not carried over (RANSAC + least-squares refits on the host): the curve set is left as it
+        is, with one warning, so that train.py's schedule keeps running."""
+        if not getattr(self, "_warned_merge", False):
+            import warnings
+            warnings.warn("curve_gaussian_b200: merge_curves is not implemented; curves are not merged")
+            self._warned_merge = True
+
+    @torch.no_grad()
+    def draw_curve(self, path, step, num_sample=200):
+        """`curve_step{step}.ply`: num_sample points per curve (gaussian_curve_model.py:713-727, without colours)."""
+        cp = self._curve_points
+        t = torch.linspace(0, 1, num_sample, device=cp.device)[None, :, None]
+        p0, p1, p2, p3 = (cp[:, i][:, None, :] for i in range(4))
+        bez = (1 - t) ** 3 * p0 + 3 * (1 - t) ** 2 * t * p1 + 3 * (1 - t) * t ** 2 * p2 + t ** 3 * p3
+        pts = torch.where(self.is_bezier[:, None, None], bez, (1 - t) * p0 + t * p3)
+        curve_io.write_ascii_points(f"{path}/curve_step{step}.ply", pts.reshape(-1, 3).cpu().numpy())
+
+    def draw_ellipsoids(self, path, step, radius=1.2):
+        """The reference dumps one open3d sphere mesh per Gaussian here (a debug visualisation); not carried over."""
+
+    def load_ply(self, path, use_train_test_exp=False):
+        raise NotImplementedError("a per-Gaussian point_cloud.ply does not determine the curve parameters "
+                                  "(the reference's loader cannot rebuild them either); use load_curves() / restore()")
 
     # ---- checkpoints and on-disk formats (curve_io) -------------------------
     def capture(self):

@@ -127,9 +127,19 @@ class CurveTopology:
         self.curve_scheduler_args = get_expon_lr_func(
             lr_init=g("lr_curve_points_init", 0.0005), lr_final=g("lr_curve_points_final", 0.000005),
             lr_delay_mult=g("position_lr_delay_mult", 0.01), max_steps=g("position_lr_max_steps", 30000))
+        # per-image exposure (train.py:228-229 steps this optimizer every iteration; unused unless train_test_exp)
+        if not isinstance(getattr(self, "_exposure", None), nn.Parameter):
+            self._exposure = nn.Parameter(torch.eye(3, 4, device=dev)[None].clone().requires_grad_(True))
+        self.exposure_optimizer = torch.optim.Adam([self._exposure])
+        self.exposure_scheduler_args = get_expon_lr_func(
+            g("exposure_lr_init", 0.01), g("exposure_lr_final", 0.001), lr_delay_steps=g("exposure_lr_delay_steps", 0),
+            lr_delay_mult=g("exposure_lr_delay_mult", 0.0), max_steps=g("iterations", 10000))
         return self.optimizer
 
     def update_learning_rate(self, iteration):
+        if getattr(self, "pretrained_exposures", None) is None and getattr(self, "exposure_optimizer", None) is not None:
+            for group in self.exposure_optimizer.param_groups:
+                group["lr"] = self.exposure_scheduler_args(iteration)
         for group in self.optimizer.param_groups:
             if group["name"] == "curve_points":
                 group["lr"] = self.curve_scheduler_args(iteration)

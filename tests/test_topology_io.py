@@ -222,3 +222,46 @@ def test_fit_curve_to_line_matches_reference_decisions():
     assert torch.equal(st["exp_avg"], torch.from_numpy(d["out_exp_avg_curve_points"]))   # moments restarted
     assert float(st["exp_avg"].abs().max()) == 0.0
     assert m.fit_curve_to_line(0.002, 0.004) == 0                                # idempotent
+
+
+def test_create_from_pcd_and_the_remaining_train_py_surface(tmp_path, monkeypatch):
+    import types
+    import warnings
+    from curve_gaussian_b200 import curve_model
+
+    def brute_dist2(p):        # mean squared distance to the 3 nearest neighbours (what distCUDA2 returns)
+        d2 = torch.cdist(p.double(), p.double()) ** 2
+        d2.fill_diagonal_(float("inf"))
+        return d2.topk(3, largest=False).values.mean(1).float()
+
+    monkeypatch.setattr(curve_model, "distCUDA2", brute_dist2)
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(30, 3, generator=g)
+    pcd = types.SimpleNamespace(points=pts.numpy(), colors=np.zeros((30, 3)))
+    cams = [types.SimpleNamespace(image_name=f"im{i:03d}") for i in range(4)]
+    m = CpuModel(0, n_gaussians=5, device="cpu").create_from_pcd(pcd, cams, spatial_lr_scale=2.5)
+    assert m._curve_points.shape == (30, 4, 3) and bool(m.is_bezier.all()) and m.spatial_lr_scale == 2.5
+    bound = 0.5 * brute_dist2(pts).clamp_min(1e-7).sqrt()
+    cp = m._curve_points.detach()
+    assert torch.allclose(cp[:, 0], pts - torch.stack([torch.zeros(30), bound, torch.zeros(30)], 1), atol=1e-6)
+    assert torch.allclose(cp[:, 3] - cp[:, 0], torch.stack([torch.zeros(30), 2 * bound, torch.zeros(30)], 1), atol=1e-6)
+    assert torch.allclose(torch.sigmoid(m._opacity), torch.full((30, 1), 0.6)) and torch.allclose(m.get_curve_width, torch.full((30, 1), 5e-3))
+    assert m.exposure_mapping == {"im000": 0, "im001": 1, "im002": 2, "im003": 3} and m._exposure.shape == (4, 3, 4)
+    assert torch.equal(m.get_exposure_from_name("im002"), m._exposure[2])
+    m.training_setup(Args())
+    m.update_learning_rate(10)
+    m.exposure_optimizer.step()          # train.py:228 steps it every iteration
+    m.oneupSHdegree()
+    assert m.active_sh_degree == 0       # max_sh_degree is 0
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m.merge_curves(0.02, 0.97)
+        m.merge_curves(0.02, 0.97)
+    assert len(w) == 1 and m._curve_points.shape[0] == 30
+    m.draw_curve(str(tmp_path), 7, num_sample=20)
+    m.draw_ellipsoids(str(tmp_path), 7)
+    back = curve_io.read_ply(str(tmp_path / "curve_step7.ply"))
+    assert len(back["x"]) == 30 * 20
+    assert np.allclose([back["x"][0], back["y"][0], back["z"][0]], cp[0, 0].numpy(), atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        m.load_ply("whatever.ply")
