@@ -2,8 +2,7 @@
 names, properties and `prepare_scaling_rot()`, with the sampling math running as the fused CUDA op in
 sampling.py (:54-198, the hot path). The training-time surgery on the curve set and the optimizer
 bookkeeping (:200-459) come from topology.CurveTopology; checkpoints and the on-disk formats (ply,
-parametric_edges.json) from curve_io. RANSAC curve merging (:462-588) and the mesh/point-cloud debug dumps
-(:643-727) are not carried over.
+parametric_edges.json) from curve_io. The open3d mesh dump (:643-711) is not carried over.
 """
 from __future__ import annotations
 
@@ -177,14 +176,6 @@ class GaussianCurveModel(CurveTopology):
         if getattr(self, "pretrained_exposures", None) is None:
             return self._exposure[self.exposure_mapping[image_name]]
         return self.pretrained_exposures[image_name]
-
-    def merge_curves(self, *args, **kwargs):
-        """Not carried over (RANSAC + least-squares refits on the host): the curve set is left as it
-        is, with one warning, so that train.py's schedule keeps running."""
-        if not getattr(self, "_warned_merge", False):
-            import warnings
-            warnings.warn("curve_gaussian_b200: merge_curves is not implemented; curves are not merged")
-            self._warned_merge = True
 
     @torch.no_grad()
     def draw_curve(self, path, step, num_sample=200):

@@ -6,8 +6,9 @@ rearrange the per-curve tensors `_curve_points/_width/_opacity/_mask/is_bezier` 
 runs as a handful of whole-tensor device ops, no per-curve host loop, and ends with `prepare_scaling_rot()` so
 the hot path sees the new curve set. Method names, arguments and results follow the reference.
 
-Not carried over: `merge_curves` (RANSAC + least-squares Bezier refits through skimage / scipy and the
-reference's edge_extraction package on the host) - a different subsystem, see DESIGN.md.
+`merge_curves` is carried over in a deterministic form: the reference draws a RANSAC consensus set before each
+line / Bezier refit (skimage, unseeded); here every sampled point of an already pre-filtered pair takes part, the
+fits are closed-form and batched (see the method).
 """
 from __future__ import annotations
 
@@ -307,3 +308,147 @@ class CurveTopology:
             self.is_bezier = self.is_bezier & ~straight
             self._adopt(self.replace_tensor_to_optimizer(cp.clone(), "curve_points"))
         return k
+
+    # ---- merging -----------------------------------------------------------------------------------------------
+    def sample_curve_points(self, sample_num=100):
+        """(B, sample_num, 3) points at t = linspace(0, 1): cubic Beziers, or the chord for straight segments
+        (get_curve_gaussians, gaussian_curve_model.py:70-78)."""
+        cp = self._curve_points.detach()
+        t = torch.linspace(0, 1, sample_num, device=cp.device)[None, :, None]
+        p0, p1, p2, p3 = (cp[:, i][:, None, :] for i in range(4))
+        bez = (1 - t) ** 3 * p0 + 3 * (1 - t) ** 2 * t * p1 + 3 * (1 - t) * t ** 2 * p2 + t ** 3 * p3
+        return torch.where(self.is_bezier[:, None, None], bez, (1 - t) * p0 + t * p3)
+
+    def _bezier_merge_candidates(self, distance_threshold, similarity_threshold, rows=2048):
+        """Edges (i, j, confidence) of the reference's end-point adjacency (gaussian_curve_model.py:469-484): some
+        end of i within 2*distance_threshold of some end of j with |cos| of the end tangents above the threshold;
+        confidence = the largest |cos| over the four end pairings. Built in row blocks, so the (2B)^2 matrices of
+        the reference never exist."""
+        cp = self._curve_points.detach()
+        B = cp.shape[0]
+        ends = (cp[:, 0], cp[:, 3])
+        tang = [cp[:, 1] - cp[:, 0], cp[:, 2] - cp[:, 3]]
+        tang = [v / (v.norm(dim=-1, keepdim=True) + 1e-6) for v in tang]
+        out = []
+        for r0 in range(0, B, rows):
+            r1 = min(B, r0 + rows)
+            adj = torch.zeros((r1 - r0, B), dtype=torch.bool, device=cp.device)
+            conf = torch.zeros((r1 - r0, B), dtype=cp.dtype, device=cp.device)
+            for a in range(2):
+                for b in range(2):
+                    sim = (tang[a][r0:r1] @ tang[b].T).abs()
+                    adj |= (torch.cdist(ends[a][r0:r1], ends[b]) < 2 * distance_threshold) & (sim > similarity_threshold)
+                    conf = torch.maximum(conf, sim)
+            i, j = adj.nonzero(as_tuple=True)
+            out.append(torch.stack([(i + r0).double(), j.double(), conf[i, j].double()], dim=1))
+        return torch.cat(out).cpu() if out else torch.zeros((0, 3), dtype=torch.float64)
+
+    def merge_curves(self, distance_threshold=0.02, similarity_threshold=0.97, sample_num=100, ransac_thresh=0.005):
+        """Join Beziers that continue each other end to end, and straight segments that are collinear and touching
+        (gaussian_curve_model.py:459-588).
+
+        Beziers: greedy pairing in index order - every curve takes its most tangent-aligned unpaired neighbour -
+        then one cubic is fitted through the 2*sample_num points of a pair, ordered along their principal axis,
+        and replaces the pair if its RMS residual stays below distance_threshold. Segments: connected components of
+        (distance <= distance_threshold, |cos| >= similarity_threshold) become the extent of their points along
+        the principal axis. A merged curve gets the mean width / opacity logit of its parts and a fresh mask.
+        Differences from the reference: its RANSAC consensus step (`ransac_thresh`, unseeded) is replaced by using
+        every sampled point; the least-squares cubic is solved in closed form (the parametrisation is fixed, so the
+        fit is linear) instead of scipy's iterative curve_fit; pairs and components are processed batched.
+        Returns the number of curves removed."""
+        cp = self._curve_points.detach()
+        dev, B = cp.device, cp.shape[0]
+        if B == 0:
+            return 0
+        pts = self.sample_curve_points(sample_num)
+        is_bez = self.is_bezier.cpu().tolist()
+        merge_mask = torch.zeros(B, dtype=torch.bool, device=dev)
+        new_cp, new_isb, parts = [], [], []
+
+        # -- Beziers: greedy pairs (host walk over the sparse candidate list, as the reference walks its matrix)
+        edges = self._bezier_merge_candidates(distance_threshold, similarity_threshold).tolist()
+        nbrs: Dict[int, list] = {}
+        for i, j, c in edges:
+            nbrs.setdefault(int(i), []).append((int(j), c))
+        taken, pairs = set(), []
+        for i in range(B):
+            if i in taken or not is_bez[i]:
+                continue
+            cand = [(j, c) for j, c in nbrs.get(i, []) if j not in taken and j != i and is_bez[j]]
+            if not cand:
+                continue
+            best = max(cand, key=lambda jc: jc[1])[0]       # first maximum in index order, like max() over the list
+            taken.update((i, best))
+            pairs.append((i, best))
+        if pairs:
+            pr = torch.tensor(pairs, device=dev)
+            P = torch.cat([pts[pr[:, 0]], pts[pr[:, 1]]], dim=1).double()                  # (K, 2S, 3)
+            C = P - P.mean(dim=1, keepdim=True)
+            axis = torch.linalg.eigh(C.transpose(1, 2) @ C).eigenvectors[..., -1]        # principal direction
+            order = (C * axis[:, None, :]).sum(-1).argsort(dim=1)
+            P = torch.gather(P, 1, order[:, :, None].expand(-1, -1, 3))
+            n = P.shape[1]
+            t = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+            basis = torch.stack([(1 - t) ** 3, 3 * (1 - t) ** 2 * t, 3 * (1 - t) * t ** 2, t ** 3], dim=1)   # (n, 4)
+            ctrl = torch.linalg.pinv(basis) @ P                                          # least squares, (K, 4, 3)
+            rmse = ((P - basis @ ctrl) ** 2).sum(-1).mean(dim=1).sqrt()
+            ok = rmse <= distance_threshold
+            for k in ok.nonzero().view(-1).tolist():
+                merge_mask[list(pairs[k])] = True
+                new_cp.append(ctrl[k].to(cp.dtype))
+                new_isb.append(True)
+                parts.append(list(pairs[k]))
+
+        # -- straight segments: connected components of "touching and parallel"
+        line_idx = (~self.is_bezier).nonzero().view(-1)
+        L = int(line_idx.numel())
+        if L > 1:
+            a, b = cp[line_idx, 0].double(), cp[line_idx, 3].double()
+            d = b - a
+
+            def seg_to_points(q):            # [i, j] = distance from segment i to point q_j
+                u = (((q[None, :, :] - a[:, None, :]) * d[:, None, :]).sum(-1) / (d * d).sum(-1)[:, None]).clamp(0, 1)
+                return (a[:, None, :] + u[..., None] * d[:, None, :] - q[None, :, :]).norm(dim=-1)
+
+            upper = torch.triu(torch.minimum(seg_to_points(a), seg_to_points(b)), diagonal=1)
+            dist = upper + upper.T           # the reference fills i < j and mirrors (edge_extraction/merging.py:84-107)
+            dn = d / d.norm(dim=-1, keepdim=True).clamp_min(1e-300)
+            adj = (dist <= distance_threshold) & ((dn @ dn.T).abs() >= similarity_threshold)
+            adj |= torch.eye(L, dtype=torch.bool, device=dev)
+            labels = torch.arange(L, device=dev)
+            while True:                      # min-label propagation: a component is named after its first member
+                nxt = torch.where(adj, labels[None, :], L).min(dim=1).values
+                nxt = torch.minimum(nxt, labels)
+                if torch.equal(nxt, labels):
+                    break
+                labels = nxt
+            for lab in labels.unique().tolist():
+                members = (labels == lab).nonzero().view(-1)
+                if members.numel() < 2:
+                    continue
+                which = line_idx[members]
+                merge_mask[which] = True
+                Q = pts[which].reshape(-1, 3).double()
+                mean = Q.mean(dim=0)
+                Cq = Q - mean
+                axis = torch.linalg.eigh(Cq.T @ Cq / Q.shape[0]).eigenvectors[:, -1]
+                proj = Cq @ axis
+                seg = torch.zeros((4, 3), dtype=cp.dtype, device=dev)    # inner control points of a segment are unused
+                seg[0], seg[3] = (mean + proj.min() * axis).to(cp.dtype), (mean + proj.max() * axis).to(cp.dtype)
+                new_cp.append(seg)
+                new_isb.append(False)
+                parts.append(which.tolist())
+
+        removed = int(merge_mask.sum())
+        if removed:
+            opac = torch.stack([self._opacity.detach()[p].mean(dim=0) for p in parts])
+            width = torch.stack([self._width.detach()[p].mean(dim=0) for p in parts])
+            k = len(parts)
+            f_dc = self._features_dc.detach()[0:1].repeat(k, 1, 1, 1)
+            f_rest = self._features_rest.detach()[0:1].repeat(k, 1, 1, 1)
+            masks = torch.ones((k,) + tuple(self._mask.shape[1:]), dtype=self._mask.dtype, device=dev)
+            self.prune_curves(merge_mask)
+            self.densification_postfix(torch.stack(new_cp), f_dc, f_rest, opac, width, masks,
+                                       torch.tensor(new_isb, dtype=torch.bool, device=dev))
+            self.prepare_scaling_rot()
+        return removed

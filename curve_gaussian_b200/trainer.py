@@ -6,7 +6,7 @@ from the reference loop are host-side only:
   * the image loss, curve smoothness and endpoint connectivity are the fused ops (loss.py, regularizers.py);
   * nothing reads a device scalar per iteration (the reference's five `.item()` calls for its progress bar,
     train.py:153-157, and the `visibility_filter.sum() > 0` tests, :114/:119); `stats()` reads them on demand;
-  * RANSAC curve merging (`merge_curves`, train.py:215) is not run (topology.py).
+  * `merge_curves` (train.py:215) runs in its deterministic, batched form (topology.py): no RANSAC draw.
 """
 from __future__ import annotations
 
@@ -54,6 +54,8 @@ class OptimizationParams:
     threshold_max_line = 0.005
     threshold_angle = 20
     threshold_angle_skip = 30
+    distance_threshold = 0.02
+    similarity_threshold = 0.97
 
     def __init__(self, **overrides):
         for k, v in overrides.items():
@@ -165,7 +167,8 @@ class TrainLoop:
             if it % 1000 == 0 and it > 3000 and it != opt.iterations:
                 m.curve_split_curvature(opt.threshold_angle, opt.threshold_angle_skip)
             if (it % 1000 == 0 and it > opt.densify_until_iter) or it == opt.iterations:
-                m.fit_curve_to_line(opt.threshold_line, opt.threshold_max_line)   # (merge_curves: not carried over)
+                m.fit_curve_to_line(opt.threshold_line, opt.threshold_max_line)
+                m.merge_curves(opt.distance_threshold, opt.similarity_threshold)
             if it < opt.iterations:
                 m.optimizer.step()
                 if not self.graph:      # (the captured step zeroes its flat gradient buffer itself)

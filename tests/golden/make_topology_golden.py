@@ -142,6 +142,43 @@ def main():
     np.savez_compressed(os.path.join(HERE, "topology_fit_line.npz"), n=12, **before, **after)
     print("fit_line", int(before["in_is_bezier"].sum()), "->", int(after["out_is_bezier"].sum()), "beziers")
 
+    # 4. merge_curves with the RANSAC consensus step replaced by "every point is an inlier" (skimage is not in this
+    #    image and the reference does not seed it): everything else - pairing, ordering, scipy's curve_fit, line
+    #    components - is the reference's own code
+    import scene.gaussian_curve_model as ref_mod
+    ref_mod.ransac = lambda pts, model, min_samples, residual_threshold, max_trials: (None, np.ones(len(pts), dtype=bool))
+    m, g = build(GaussianCurveModel, 24, 12, seed=41, line_fraction=0.0)
+    with torch.no_grad():
+        base, _, _, _ = synth.random_curves(14, seed=43)
+        halves = []
+        for c in base[:8]:                                   # 8 smooth curves cut in two -> 16 mergeable halves
+            l, r = m.de_casteljau_split(c[None], torch.tensor([[0.5]]), torch.ones(1, dtype=torch.bool))
+            halves += [l[0], r[0]]
+        segs = []
+        for c in base[8:14]:                                 # 6 chords cut in three collinear segments
+            a, b = c[0], c[3]
+            for k in range(3):
+                p, q = a + (b - a) * k / 3, a + (b - a) * (k + 1) / 3
+                segs.append(torch.stack([p, p + (q - p) / 3, p + 2 * (q - p) / 3, q]))
+        extra = m._curve_points[:24 - 16].detach().clone()   # unrelated curves
+        allc = torch.stack(halves + segs + list(extra))
+        perm = torch.randperm(allc.shape[0], generator=g)
+        isb = torch.tensor([True] * 16 + [False] * 18 + [True] * extra.shape[0])[perm]
+        allc = allc[perm]
+    B2 = allc.shape[0]
+    m2, g = build(GaussianCurveModel, B2, 12, seed=45, line_fraction=0.0)
+    with torch.no_grad():
+        m2._curve_points.copy_(allc)
+    m2.is_bezier = isb.clone()
+    m2.prepare_scaling_rot()
+    before = state(m2, "in_")
+    with torch.no_grad():
+        m2.merge_curves(0.02, 0.97)
+    after = state(m2, "out_")
+    np.savez_compressed(os.path.join(HERE, "topology_merge.npz"), n=12, **before, **after)
+    print("merge", before["in_curve_points"].shape[0], "->", after["out_curve_points"].shape[0], "curves,",
+          int(after["out_is_bezier"].sum()), "beziers")
+
     for name, fn in cases.items():
         m, g = build(GaussianCurveModel, 60, 12, seed=21, line_fraction=0.25)
         before = state(m, "in_")

@@ -226,7 +226,6 @@ def test_fit_curve_to_line_matches_reference_decisions():
 
 def test_create_from_pcd_and_the_remaining_train_py_surface(tmp_path, monkeypatch):
     import types
-    import warnings
     from curve_gaussian_b200 import curve_model
 
     def brute_dist2(p):        # mean squared distance to the 3 nearest neighbours (what distCUDA2 returns)
@@ -253,11 +252,6 @@ def test_create_from_pcd_and_the_remaining_train_py_surface(tmp_path, monkeypatc
     m.exposure_optimizer.step()          # train.py:228 steps it every iteration
     m.oneupSHdegree()
     assert m.active_sh_degree == 0       # max_sh_degree is 0
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        m.merge_curves(0.02, 0.97)
-        m.merge_curves(0.02, 0.97)
-    assert len(w) == 1 and m._curve_points.shape[0] == 30
     m.draw_curve(str(tmp_path), 7, num_sample=20)
     m.draw_ellipsoids(str(tmp_path), 7)
     back = curve_io.read_ply(str(tmp_path / "curve_step7.ply"))
@@ -265,3 +259,44 @@ def test_create_from_pcd_and_the_remaining_train_py_surface(tmp_path, monkeypatc
     assert np.allclose([back["x"][0], back["y"][0], back["z"][0]], cp[0, 0].numpy(), atol=1e-6)
     with pytest.raises(NotImplementedError):
         m.load_ply("whatever.ply")
+
+
+def test_merge_curves_matches_the_reference_without_its_ransac_step():
+    """Golden: the reference's merge_curves with `ransac` returning every point as an inlier (skimage is absent here
+    and the reference leaves it unseeded). Ours fits in closed form, so new control points agree to ~1e-5 and up to
+    the orientation of the principal axis (an eigenvector's sign), i.e. up to reversing the control polygon."""
+    d = load("merge")
+    m = model_from(d)
+    removed = m.merge_curves(0.02, 0.97)
+    out_cp, out_isb = torch.from_numpy(d["out_curve_points"]), torch.from_numpy(d["out_is_bezier"])
+    B_in, B_out = d["in_curve_points"].shape[0], out_cp.shape[0]
+    assert m._curve_points.shape[0] == B_out and torch.equal(m.is_bezier, out_isb)
+    kept = B_in - removed
+    assert removed == 34 and kept == 8                                   # 16 halves + 18 segments went, 8 + 6 came
+    got = m._curve_points.detach()
+    assert torch.equal(got[:kept], out_cp[:kept])                        # untouched curves, same order
+    for k in range(kept, B_out):
+        a, b = got[k], out_cp[k]
+        if bool(out_isb[k]):
+            err = min((a - b).abs().max(), (a.flip(0) - b).abs().max())
+        else:
+            assert float(a[1:3].abs().max()) == 0.0 and float(b[1:3].abs().max()) == 0.0
+            ends_a, ends_b = a[[0, 3]], b[[0, 3]]
+            err = min((ends_a - ends_b).abs().max(), (ends_a.flip(0) - ends_b).abs().max())
+        assert float(err) < 2e-5, (k, float(err))
+    assert torch.allclose(m._opacity.detach(), torch.from_numpy(d["out_opacity"]), atol=1e-6)
+    assert torch.allclose(m._width.detach(), torch.from_numpy(d["out_width"]), atol=1e-6)
+    assert torch.equal(m._mask.detach(), torch.from_numpy(d["out_mask"]))
+    st = [m.optimizer.state[g["params"][0]] for g in m.optimizer.param_groups if g["name"] == "curve_points"][0]
+    assert torch.equal(st["exp_avg"], torch.from_numpy(d["out_exp_avg_curve_points"]))
+    assert m._xyz.shape[0] == B_out * m.n_gaussians
+    # a merged Bezier traces its two halves: every sampled point of the inputs lies within 1e-3 of the new curve
+    t = torch.linspace(0, 1, 400)[:, None, None].double()
+    c = got[kept:][out_isb[kept:]].double()
+    dense = ((1 - t) ** 3 * c[:, 0] + 3 * (1 - t) ** 2 * t * c[:, 1] + 3 * (1 - t) * t ** 2 * c[:, 2] + t ** 3 * c[:, 3]).reshape(-1, 3)
+    src = model_from(d)
+    halves = src.sample_curve_points(50)[torch.from_numpy(d["in_is_bezier"])].double().reshape(-1, 3)
+    near = torch.cdist(halves, dense).min(dim=1).values
+    assert float((near < 1e-3).double().mean()) > 16 / 24 - 1e-9       # the 16 merged halves (8 unrelated curves remain)
+    m.merge_curves(0.02, 0.97)                                           # a second pass runs on the merged set
+    assert m._xyz.shape[0] == m._curve_points.shape[0] * m.n_gaussians
