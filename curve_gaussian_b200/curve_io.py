@@ -6,8 +6,9 @@
 * `save_gaussians_ply`: the per-Gaussian `point_cloud.ply` (scene/gaussian_model.py:383-400; same attribute
   names and order, binary little-endian float32), written without the `plyfile` dependency.
 * `extract_curves`: `parametric_edges.json` + `edge_points.ply` as train.py:250-293 writes them for the
-  evaluation scripts (the endpoint merging and visibility filtering options of that function live in the
-  reference's edge_extraction package and are not part of this port).
+  evaluation scripts, including the end-point merging (`merge_endpoints`, edge_extraction/merging.py:10-55); the
+  visibility filtering option (`opt.visible_checking`, off by default, needs the dataset's edge maps) is not part
+  of this port.
 """
 from __future__ import annotations
 
@@ -167,17 +168,50 @@ def sample_edges(edge_dict: dict, sample_resolution: float = 0.005) -> np.ndarra
     return np.concatenate(out, axis=0).astype(np.float32) if out else np.zeros((0, 3), np.float32)
 
 
-def edge_dict(model) -> dict:
+def merge_endpoints(lines: np.ndarray, curves: np.ndarray, distance_threshold: float):
+    """Snap end points that lie within distance_threshold of each other (transitively) to their common mean
+    (edge_extraction/merging.py:10-55). lines: (Nl,6) end-point pairs, curves: (Nc,12) control polygons; only the
+    first and last control point of a curve move. Returns the two arrays with merged end points."""
+    lines = np.asarray(lines, dtype=np.float64).reshape(-1, 6)
+    curves = np.asarray(curves, dtype=np.float64).reshape(-1, 12)
+    pts = np.concatenate([lines.reshape(-1, 3), curves[:, [0, 1, 2, 9, 10, 11]].reshape(-1, 3)], axis=0)
+    n = len(pts)
+    if n == 0:
+        return lines, curves
+    adj = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=-1) <= distance_threshold
+    labels = np.arange(n)
+    while True:                                   # min-label propagation = connected components
+        nxt = np.where(adj, labels[None, :], n).min(axis=1)
+        if np.array_equal(nxt, labels):
+            break
+        labels = nxt
+    sums = np.zeros((n, 3))
+    np.add.at(sums, labels, pts)
+    counts = np.bincount(labels, minlength=n)[:, None]
+    merged = np.where(counts[labels] > 1, sums[labels] / np.maximum(counts[labels], 1), pts)
+    out_lines = merged[: 2 * len(lines)].reshape(-1, 6)
+    ends = merged[2 * len(lines):].reshape(-1, 6)
+    out_curves = curves.copy()
+    out_curves[:, :3], out_curves[:, 9:] = ends[:, :3], ends[:, 3:]
+    return out_lines, out_curves
+
+
+def edge_dict(model, merge_endpoints_flag: bool = False, distance_threshold: float = 0.015) -> dict:
     """{'curves_ctl_pts': (Nb,4,3) lists, 'lines_end_pts': (Nl,6) lists} (train.py:252-271, extract_para_edge.py:83-100)."""
     cp = model.get_curve_points.detach()
     isb = model.is_bezier
-    return {"curves_ctl_pts": cp[isb].cpu().double().numpy().reshape(-1, 4, 3).tolist(),
-            "lines_end_pts": cp[~isb][:, [0, -1], :].reshape(-1, 6).cpu().double().numpy().tolist()}
+    curves = cp[isb].cpu().double().numpy().reshape(-1, 12)
+    lines = cp[~isb][:, [0, -1], :].reshape(-1, 6).cpu().double().numpy()
+    if merge_endpoints_flag:
+        lines, curves = merge_endpoints(lines, curves, distance_threshold)
+    return {"curves_ctl_pts": curves.reshape(-1, 4, 3).tolist(), "lines_end_pts": lines.tolist()}
 
 
-def extract_curves(model, model_path: str, sample_resolution: float = 0.005) -> Tuple[np.ndarray, dict]:
-    """Write `parametric_edges.json` and `edge_points.ply` under model_path (train.py:250-293)."""
-    d = edge_dict(model)
+def extract_curves(model, model_path: str, sample_resolution: float = 0.005, merge_endpoints_flag: bool = True,
+                   distance_threshold: float = 0.015) -> Tuple[np.ndarray, dict]:
+    """Write `parametric_edges.json` and `edge_points.ply` under model_path (train.py:250-293; end points closer
+    than distance_threshold are merged first, `opt.merge_endpoints_flag`, on by default as in the reference)."""
+    d = edge_dict(model, merge_endpoints_flag, distance_threshold)
     pts = sample_edges(d, sample_resolution)
     write_ascii_points(os.path.join(model_path, "edge_points.ply"), pts)
     with open(os.path.join(model_path, "parametric_edges.json"), "w") as f:

@@ -14,6 +14,7 @@ and the parameters themselves; gradients land in the parameters' existing `.grad
 """
 from __future__ import annotations
 
+import gc
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -60,6 +61,11 @@ class GraphedStep:
     policy has to be active (one is created if none is given). `calibrate` is an optional list of callables
     run before the capture, each followed by one eager `fn()`, to show the policy the largest R it will meet
     (e.g. one per distinct view: `lambda: scam.load(cam)`).
+
+    Autograd graphs over the same parameters that were built on another stream must be gone when the capture
+    starts (their AccumulateGrad nodes would tie the captured backward to that stream); `fn` itself should
+    therefore rebuild everything it differentiates through, as `GaussianCurveModel.prepare_scaling_rot()` does
+    by dropping the previous sampled tensors first.
     """
 
     def __init__(self, fn: Callable[[], object], policy: Optional[_rz.CapacityBinning] = None, warmup: int = 2,
@@ -98,10 +104,25 @@ class GraphedStep:
                 else:
                     raise _rz.CapacityOverflow("the binning capacity did not settle during warm-up")
             # capture on the stream the warm-up ran on: autograd's AccumulateGrad nodes remember the stream they
-            # were created on, and a node from the warm-up that syncs with another stream invalidates the capture
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
-                self.out = self.fn()
+            # were created on, and a node that syncs with another stream (worst case the legacy default stream,
+            # cudaErrorStreamCaptureImplicit) invalidates the capture. Such a node only exists while an autograd
+            # graph from before the warm-up is still alive; if a capture fails, drop what can be dropped and retry.
+            for attempt in range(3):
+                self.graph = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(self.graph, stream=side):
+                        self.out = self.fn()
+                    break
+                except RuntimeError:
+                    self.graph = self.out = None
+                    torch.cuda.set_stream(cur)     # (a failed capture_end leaves torch's stream context un-exited)
+                    if attempt == 2:
+                        raise
+                    gc.collect()
+                    torch.cuda.synchronize()
+                    with torch.cuda.stream(side):
+                        self.fn()
+                    side.synchronize()
             cur.wait_stream(side)
         finally:
             switch.disable()

@@ -188,7 +188,7 @@ def test_ply_and_parametric_edges_files(tmp_path):
     assert np.array_equal(np.stack([got[f"rot_{i}"] for i in range(4)], 1), m._rotation.detach().numpy())
     assert np.allclose(got["opacity"], m._opacity.detach().repeat_interleave(6).numpy(), atol=1e-6)
 
-    pts, d = curve_io.extract_curves(m, str(tmp_path))
+    pts, d = curve_io.extract_curves(m, str(tmp_path), merge_endpoints_flag=False)
     on_disk = json.load(open(tmp_path / "parametric_edges.json"))
     assert on_disk == d
     nb, nl = int(isb.sum()), int((~isb).sum())
@@ -300,3 +300,15 @@ def test_merge_curves_matches_the_reference_without_its_ransac_step():
     assert float((near < 1e-3).double().mean()) > 16 / 24 - 1e-9       # the 16 merged halves (8 unrelated curves remain)
     m.merge_curves(0.02, 0.97)                                           # a second pass runs on the merged set
     assert m._xyz.shape[0] == m._curve_points.shape[0] * m.n_gaussians
+
+
+def test_merge_endpoints_matches_reference():
+    d = np.load(os.path.join(GOLD, "merge_endpoints.npz"))
+    lines, curves = curve_io.merge_endpoints(d["lines"], d["curves"], 0.015)
+    assert np.allclose(lines, d["out_lines"], atol=1e-12) and np.allclose(curves, d["out_curves"], atol=1e-12)
+    assert np.array_equal(curves[:, 3:9], d["curves"][:, 3:9])                  # inner control points never move
+    assert np.array_equal(lines[-5:], d["lines"][-5:])                          # isolated segments untouched
+    e_l, e_c = curve_io.merge_endpoints(np.zeros((0, 6)), np.zeros((0, 12)), 0.015)
+    assert e_l.shape == (0, 6) and e_c.shape == (0, 12)
+    only_c = curve_io.merge_endpoints(np.zeros((0, 6)), d["curves"], 0.015)[1]
+    assert only_c.shape == d["curves"].shape
