@@ -61,3 +61,55 @@ def test_static_camera_takes_only_views_of_its_own_shape():
     assert ptrs == (sc.world_view_transform.data_ptr(), sc.full_proj_transform.data_ptr(), sc.camera_center.data_ptr())
     with pytest.raises(ValueError):
         sc.load(other)
+
+
+def test_graphed_step_control_flow_with_a_fake_cuda(monkeypatch):
+    """Host logic of GraphedStep.capture / verify (warm-up, capture, retry after a failed capture, re-capture after an
+    overflow) with torch.cuda's stream / graph objects replaced by fakes - the real thing runs in the GPU tests."""
+    import contextlib
+    import torch
+    from curve_gaussian_b200 import graph as G
+
+    class FakeStream:
+        def wait_stream(self, other): pass
+        def synchronize(self): pass
+
+    class FakeGraph:
+        replays = 0
+        def replay(self): FakeGraph.replays += 1
+
+    fail_first = {"n": 1}
+
+    @contextlib.contextmanager
+    def fake_graph_ctx(g, stream=None):
+        yield
+        if fail_first["n"] > 0:
+            fail_first["n"] -= 1
+            raise RuntimeError("CUDA error: operation failed due to a previous error during capture")
+
+    cur = FakeStream()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: cur)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", fake_graph_ctx)
+    restored = []
+    monkeypatch.setattr(torch.cuda, "set_stream", restored.append)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+
+    calls, prepared = [], []
+    pol = rz.CapacityBinning(granule=64)
+    gs = G.GraphedStep(lambda: calls.append(rz._policy) or "out", policy=pol,
+                       calibrate=[lambda: prepared.append(1), lambda: prepared.append(2)])
+    assert gs.replay() == "out"                                  # captures on first use
+    assert prepared == [1, 2] and gs.captures == 1 and FakeGraph.replays == 1
+    assert restored == [cur]                                     # the failed first capture put the stream back
+    assert len(calls) == 2 + 2 + 1 + 1 + 1                       # calibrate, warm-up, failed capture, re-warm, capture
+    assert all(c is pol for c in calls) and rz._policy is None   # policy active inside, restored outside
+    assert gs.verify() and gs.captures == 1
+    key = (10, 8, 8)
+    pol.learn(key, 100)
+    slot = pol._static[key]
+    slot[0], slot[1], slot[2] = 500, 1, 128                      # what a replay that overflowed leaves behind
+    assert not gs.verify() and gs.captures == 2 and pol.capacity(key) >= 500
+    assert gs.verify()
