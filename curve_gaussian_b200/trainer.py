@@ -95,6 +95,8 @@ class TrainLoop:
         # whenever the curve set or the set of active loss terms changes; all views must share size and FoV
         self.graph = bool(graph)
         self.captures = 0
+        self.overflows = 0          # graph mode: how often a periodic check found replays over the captured capacity
+        self.verify_every = 64
         self._gs = self._sig = self._fg = None
         if self.graph:
             self._policy = _rz.CapacityBinning()
@@ -223,7 +225,14 @@ class TrainLoop:
             self.captures += 1
         self._scam.load(cam)
         self._gt.copy_(gt, non_blocking=True)
-        return self._gs.replay()
+        out = self._gs.replay()
+        if it % self.verify_every == 0:
+            # a view with more tile-instances than the captured capacity renders from a truncated list (the farthest
+            # instances are dropped); look at the counters now and then and re-capture with more room if it happened
+            torch.cuda.current_stream().synchronize()
+            if not self._gs.verify():
+                self.overflows += 1
+        return out
 
     def verify(self) -> bool:
         """Graph mode, after a synchronisation: False if recent replays overflowed the captured binning capacity
