@@ -70,6 +70,20 @@ class PipelineParams:
     render_geo = True
 
 
+def opacity_regulariser(opacity: torch.Tensor, visible: torch.Tensor) -> torch.Tensor:
+    """mean over the visible Gaussians of log(1 + o^2 / 0.5) (train.py:114-117), 0 when none is visible. A masked
+    mean: the same value and gradient as the reference's `opacity[visibility_filter]` without the host-synchronising
+    boolean indexing and `.sum() > 0` test."""
+    vis = visible.view(-1, 1).to(opacity.dtype)
+    return (torch.log(1 + opacity ** 2 / 0.5) * vis).sum() / vis.sum().clamp_min(1.0)
+
+
+def width_regulariser(width: torch.Tensor, width_thr: float = 0.005) -> torch.Tensor:
+    """mean excess over width_thr of the curves at least that wide (train.py:126-131), 0 when there is none."""
+    over = (width >= width_thr).to(width.dtype)
+    return ((width - width_thr) * over).sum() / over.sum().clamp_min(1.0)
+
+
 class TrainLoop:
     """`TrainLoop(model, cameras, targets, opt).step()` = one iteration of train.py's loop body.
 
@@ -115,17 +129,11 @@ class TrainLoop:
                                          lambda_dssim=opt.lambda_dssim, clamp=True)}
         if iteration >= opt.densify_until_iter:
             terms["mask"] = opt.lambda_mask * torch.sigmoid(m._mask).mean()
-        # opacity regulariser over the visible Gaussians (train.py:114-117); a masked mean instead of the
-        # reference's host-synchronising boolean indexing, same value
-        vis = (pkg["radii"] > 0).view(-1, 1).float()
-        opa = torch.log(1 + m.get_opacity ** 2 / 0.5)
-        terms["opacity"] = opt.opacity_loss_weight * (opa * vis).sum() / vis.sum().clamp_min(1.0)
+        terms["opacity"] = opt.opacity_loss_weight * opacity_regulariser(m.get_opacity, pkg["radii"] > 0)
         if opt.lambda_curve_smo > 0:
             terms["curve_smo"] = opt.lambda_curve_smo * curve_smoothness(m._rotation, m.n_gaussians)
         if opt.lambda_width > 0:
-            w = m.get_curve_width
-            over = (w >= 0.005).float()
-            terms["width"] = opt.lambda_width * ((w - 0.005) * over).sum() / over.sum().clamp_min(1.0)
+            terms["width"] = opt.lambda_width * width_regulariser(m.get_curve_width)
         if opt.lambda_points_conn > 0 and iteration > opt.conn_from_iter:
             terms["curve_conn"] = opt.lambda_points_conn * endpoint_connectivity(m.get_curve_points, 0.05)
         total = terms["image"]

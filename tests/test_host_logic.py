@@ -113,3 +113,31 @@ def test_graphed_step_control_flow_with_a_fake_cuda(monkeypatch):
     slot[0], slot[1], slot[2] = 500, 1, 128                      # what a replay that overflowed leaves behind
     assert not gs.verify() and gs.captures == 2 and pol.capacity(key) >= 500
     assert gs.verify()
+
+
+def test_masked_mean_regularisers_equal_the_reference_formulations():
+    """trainer.opacity_regulariser / width_regulariser against train.py:114-117 and :126-131 written with boolean
+    indexing, values and gradients, including the empty cases."""
+    import torch
+    from curve_gaussian_b200.trainer import opacity_regulariser, width_regulariser
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(200, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    visible = torch.rand(200, generator=g) > 0.4
+    ours = opacity_regulariser(torch.sigmoid(logits), visible)
+    (ga,) = torch.autograd.grad(ours, logits)
+    ref = torch.log(1 + torch.sigmoid(logits)[visible] ** 2 / 0.5).mean()
+    (gb,) = torch.autograd.grad(ref, logits)
+    assert torch.allclose(ours, ref, rtol=1e-12) and torch.allclose(ga, gb, rtol=1e-10, atol=1e-15)
+    none = opacity_regulariser(torch.sigmoid(logits), torch.zeros(200, dtype=torch.bool))
+    assert float(none) == 0.0 and float(torch.autograd.grad(none, logits)[0].abs().max()) == 0.0
+
+    logw = (torch.randn(50, 1, generator=g, dtype=torch.float64) * 0.5 + torch.log(torch.tensor(5e-3))).requires_grad_(True)
+    w = torch.exp(logw)
+    ours = width_regulariser(w)
+    (ga,) = torch.autograd.grad(ours, logw, retain_graph=True)
+    mask = w >= 0.005
+    assert 0 < int(mask.sum()) < 50
+    ref = (w[mask] - 0.005).mean()
+    (gb,) = torch.autograd.grad(ref, logw)
+    assert torch.allclose(ours, ref, rtol=1e-12) and torch.allclose(ga, gb, rtol=1e-10, atol=1e-18)
+    assert float(width_regulariser(torch.full((5, 1), 1e-3))) == 0.0
