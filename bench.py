@@ -343,10 +343,18 @@ def run_ours(a):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
         except Exception:
             pass
+        ncu_fig = None
+        try:
+            ncu_fig = json.load(open(os.path.join(ROOT, "profiles", "limiters.json"))).get(dom)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms": round(per_stage[dom], 4), "algorithmic_bytes": alg_bytes[dom],
-                    "share_of_step": round(per_stage_step[dom] / ms_prof_step, 3)}
+                    "share_of_step": round(per_stage_step[dom] / ms_prof_step, 3),
+                    # from the committed `ncu --set full` capture (profiles/), not measured in this run: what actually
+                    # limits the kernel when the HBM fraction is low
+                    "ncu": ncu_fig}
     bytes_view = 264 * P + 148 * (R or 0) + 64 * Npix + 88 * P + 20 * Npix
     e2e_frac = bytes_view * value / 1e9 / peak
 

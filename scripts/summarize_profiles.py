@@ -5,6 +5,7 @@
   profiles/<prefix>_ncu_launches.csv                    the raw launch list
   profiles/<prefix>_ncu_full_summary.txt                key `--set full` metrics per kernel
   profiles/traffic.json                                 dram read+write bytes per launch (bench.py's roofline.traffic)
+  profiles/limiters.json                                issue-slot / DRAM / occupancy figures per stage (bench.py's roofline.ncu)
 usage: scripts/summarize_profiles.py gpurun_out/<tag> <prefix>"""
 import collections
 import csv
@@ -68,6 +69,7 @@ if os.path.exists(rep):
             "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
     units = dict(zip(hdr, rows[1]))
     traffic = {}
+    limiters = {}     # per stage: what ncu says keeps the kernel busy (read by bench.py next to roofline.traffic)
     stage_of = {"blend_bwd": "blend_bwd", "blend_fwd": "blend_fwd", "gather_records": "gather_records",
                 "preprocess_fwd": "preprocess_fwd", "preprocess_bwd": "preprocess_bwd"}
     seen = collections.Counter()
@@ -88,10 +90,16 @@ if os.path.exists(rep):
                 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(units.get("dram__bytes_read.sum", "Mbyte"), 1e6)
                 if base in stage_of and stage_of[base] not in traffic:
                     traffic[stage_of[base]] = int(mb * scale)
+                    limiters[stage_of[base]] = {
+                        "issue_active_pct": round(float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]), 1),
+                        "dram_pct_of_peak": round(float(d["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]), 1),
+                        "warps_active_pct": round(float(d["sm__warps_active.avg.pct_of_peak_sustained_active"]), 1),
+                        "registers": int(float(d["launch__registers_per_thread"]))}
                 if base == "sort_onesweep_pass":
                     traffic["radix_sort"] = traffic.get("radix_sort", 0) + int(mb * scale)
             except Exception:
                 pass
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    json.dump(limiters, open(os.path.join(P, "limiters.json"), "w"), indent=1)
     print("traffic", traffic)
 print("wrote summaries for", src, "->", P)
