@@ -18,6 +18,8 @@ constexpr int BLEND_WARPS = 8;
 constexpr int BLEND_THREADS = BLEND_WARPS * 32;
 constexpr int BLEND_SUBS = 8 / BLEND_WARPS;
 constexpr int BLEND_ROWS = (BLEND_WARPS / 2) * 4;   // pixel rows per CTA
+constexpr int RING_CLASSES = 32;   // size classes of the 8x4 blocks' candidate lists (see ImgState::cls_count)
+static_assert(BLEND_SUBS == 1, "the block candidate lists (blend_ring.cuh) assume one blend CTA per tile");
 
 void set_error(const char* fmt, ...);
 
@@ -219,8 +221,14 @@ struct ImgState {
   uint32_t* n_contrib;
   uint2* ranges;
   uint32_t* tile_maxc;  // per blend CTA (tile * BLEND_SUBS + sub): max n_contrib over its pixels (backward start)
-  uint32_t* tile_order; // blend CTA ids, longest list first: the launch order of the forward blend CTAs
-  uint32_t* tile_order_bwd;  // same by tile_maxc (the part of the list the backward really walks)
+  uint32_t* tile_order; // blend CTA ids, longest list first: the launch order of the blend CTAs (forward, and the
+                        // lane-per-pixel backward)
+  // 8x4 pixel blocks (8 per tile, block id = tile * 8 + warp), written by blend_fwd for the ring backward:
+  uint32_t* blk_cnt;    // entries of the block's candidate list (BinKeep::cand) that lie below the block's last contributor
+  uint32_t* cls_count;  // [RING_CLASSES] non-empty blocks per size class (class = half-octave of blk_cnt), then
+                        // [RING_CLASSES], [RING_CLASSES + 1] = work / exit counters of blend_bwd_ring (left at zero by it);
+                        // zero-filled together with `ranges` at the start of every forward
+  uint32_t* cls_list;   // [RING_CLASSES][tiles * 8] block ids per class, in arrival order
   static ImgState carve(void* base, int W, int H, size_t* bytes) {
     Carver c(base);
     ImgState s;
@@ -229,9 +237,11 @@ struct ImgState {
     s.final_T = c.take<float>(npix);
     s.n_contrib = c.take<uint32_t>(npix);
     s.ranges = c.take<uint2>(tiles);
+    s.cls_count = c.take<uint32_t>(RING_CLASSES + 32);   // directly behind ranges: one memset clears both
     s.tile_maxc = c.take<uint32_t>(tiles * BLEND_SUBS);
     s.tile_order = c.take<uint32_t>(tiles * BLEND_SUBS);
-    s.tile_order_bwd = c.take<uint32_t>(tiles * BLEND_SUBS);
+    s.blk_cnt = c.take<uint32_t>(tiles * 8);
+    s.cls_list = c.take<uint32_t>(size_t(RING_CLASSES) * tiles * 8);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return s;
   }
@@ -240,11 +250,16 @@ struct ImgState {
 struct BinKeep {
   Rec* rec;
   uint32_t* point_list;
+  // Candidate lists of the 8x4 pixel blocks: block b (0..7) of a tile whose range is [x, y) owns
+  // cand[8 * x + b * (y - x) ...]: the tile-relative list positions, ascending, of the instances that passed the
+  // forward's block_candidate test for that block (written by blend_fwd, consumed back to front by blend_bwd_ring).
+  uint32_t* cand;
   static BinKeep carve(void* base, int64_t R, size_t* bytes) {
     Carver c(base);
     BinKeep b;
     b.rec = c.take<Rec>(R + 1);
     b.point_list = c.take<uint32_t>(R + 1);
+    b.cand = c.take<uint32_t>(8 * size_t(R + 1));
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }

@@ -318,15 +318,28 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* _
   if (tid == 0) s_max = 1;
   __syncthreads();
   auto length = [&](uint32_t t) { if (maxc) return maxc[t]; const uint2 r = ranges[t / BLEND_SUBS]; return r.y - r.x; };
+  // every pass reads the lengths in batches of 8 independent loads per thread (one CTA: latency, not bandwidth)
   uint32_t mx = 0;
-  for (uint32_t t = tid; t < ntiles; t += 1024) mx = max(mx, length(t));
+  for (uint32_t base = 0; base < ntiles; base += 8192) {
+    uint32_t len[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint32_t t = base + k * 1024 + tid; len[k] = t < ntiles ? length(t) : 0u; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = max(mx, len[k]);
+  }
   mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) atomicMax(&s_max, mx);
   __syncthreads();
   const uint32_t top = s_max;
   // bucket 0 = longest lists
   auto bucket = [&](uint32_t len) { return 1023u - uint32_t((uint64_t(len) * 1023u) / top); };
-  for (uint32_t t = tid; t < ntiles; t += 1024) atomicAdd(&s_cnt[bucket(length(t))], 1u);
+  for (uint32_t base = 0; base < ntiles; base += 8192) {
+    uint32_t len[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint32_t t = base + k * 1024 + tid; len[k] = t < ntiles ? length(t) : 0u; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (base + k * 1024 + tid < ntiles) atomicAdd(&s_cnt[bucket(len[k])], 1u);
+  }
   __syncthreads();
   // exclusive scan of the 1024 bucket counts
   const uint32_t v = s_cnt[tid];
@@ -343,8 +356,16 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* _
   __syncthreads();
   s_cnt[tid] = s_w[w] + inc - v;   // first output slot of the bucket
   __syncthreads();
-  for (uint32_t t = tid; t < ntiles; t += 1024)
-    tile_order[atomicAdd(&s_cnt[bucket(length(t))], 1u)] = t;   // order inside a bucket is irrelevant
+  for (uint32_t base = 0; base < ntiles; base += 8192) {
+    uint32_t len[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint32_t t = base + k * 1024 + tid; len[k] = t < ntiles ? length(t) : 0u; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t t = base + k * 1024 + tid;
+      if (t < ntiles) tile_order[atomicAdd(&s_cnt[bucket(len[k])], 1u)] = t;   // order inside a bucket is irrelevant
+    }
+  }
 }
 
 // BLEND_SUBS CTAs per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block. The tile's
@@ -360,7 +381,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, CG_FWD_CTAS * (256 / BLEND_THRE
 blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int grid_x,
           const Rec* __restrict__ rec, int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-          uint32_t* __restrict__ tile_maxc) {
+          uint32_t* __restrict__ tile_maxc, uint32_t* __restrict__ cand_lists, uint32_t* __restrict__ blk_cnt,
+          uint32_t* __restrict__ cls_count, uint32_t* __restrict__ cls_list, uint32_t nblocks) {
   pdl_wait();
   __shared__ __align__(128) Rec s_rec[2][BATCH];
   __shared__ __align__(8) uint64_t s_full[2];
@@ -401,6 +423,11 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   float T = 1.0f, C = 0.f, invd_acc = 0.f;
   float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3v = 0.f;
   uint32_t last_contributor = 0;
+  // candidate list of this warp's 8x4 block (BinKeep::cand): tile-relative positions of the instances that pass the
+  // block test, in list order; cand_eff = how many of them lie at or below the block's last contributor
+  // (32-bit offsets into cand_lists: the kernel runs at 40 registers)
+  const uint32_t cand_start = 8u * range.x + (sub * BLEND_WARPS + warp) * uint32_t(total);
+  uint32_t cand_off = cand_start, cand_eff = cand_start;
 
   int todo = total;
   for (int b = 0; b < rounds; ++b, todo -= BATCH) {
@@ -430,6 +457,11 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
         cand = block_candidate(ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, bx0, bx1, by0, by1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, cand);
+      if (cand) {
+        uint32_t below;   // candidates in lower lanes (shl clamps: lane 0 shifts everything out)
+        asm("shl.b32 %0, %1, %2;" : "=r"(below) : "r"(mask), "r"(32u - lane));
+        cand_lists[cand_off + __popc(below)] = pos0 + uint32_t(idx);
+      }
       while (mask) {
         const int j = r + __ffs(int(mask)) - 1;
         mask &= mask - 1;
@@ -462,6 +494,14 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
           }
         }
       }
+      const uint32_t mask0 = __ballot_sync(0xffffffffu, cand);   // again: the walk consumed `mask`, and a register is dearer than a vote
+      if (mask0) {
+        // the block's last contributor so far lies in this chunk <=> it is newer than the chunk's first position
+        const uint32_t mc_now = __reduce_max_sync(0xffffffffu, last_contributor);
+        const uint32_t first = pos0 + uint32_t(r);
+        if (mc_now > first) cand_eff = cand_off + __popc(mask0 & (0xffffffffu >> (31u - (mc_now - 1u - first))));
+        cand_off += __popc(mask0);
+      }
     }
   }
 
@@ -480,7 +520,18 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   }
   uint32_t mc = inside ? last_contributor : 0u;
   mc = __reduce_max_sync(0xffffffffu, mc);
-  if (lane == 0) atomicMax(&s_maxc, mc);
+  if (lane == 0) {
+    atomicMax(&s_maxc, mc);
+    // the block joins the list of its size class (half octaves of the candidate count): the ring backward takes the
+    // classes largest first, which is all the ordering its greedy scheduling needs
+    const uint32_t n = cand_eff - cand_start, bid = tile * 8 + sub * BLEND_WARPS + warp;
+    blk_cnt[bid] = n;
+    if (n) {
+      const uint32_t msb = 31u - uint32_t(__clz(int(n)));
+      const uint32_t cls = min(uint32_t(RING_CLASSES - 1), 2u * msb + (msb ? ((n >> (msb - 1u)) & 1u) : 0u));
+      cls_list[size_t(cls) * nblocks + atomicAdd(&cls_count[cls], 1u)] = bid;
+    }
+  }
   __syncthreads();
   if (tid == 0) tile_maxc[cta] = s_maxc;
 }
@@ -567,7 +618,8 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
   const int64_t nblk = (P + 255) / 256;
   const size_t tiles = size_t(gx) * gy;
 
-  CG_CUDA(cudaMemsetAsync(im.ranges, 0, tiles * sizeof(uint2), st));
+  // tile ranges, and behind them the size-class counters of the ring backward
+  CG_CUDA(cudaMemsetAsync(im.ranges, 0, size_t(reinterpret_cast<char*>(im.cls_count + RING_CLASSES + 32) - reinterpret_cast<char*>(im.ranges)), st));
   if (R > 0) {
     int rc;
     // the Gaussians were depth-sorted and their offsets scanned in that order by cg_raster_fwd_geom;
@@ -590,18 +642,15 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     CG_LAUNCH_CHECK(s->debug, st);
   }
   const dim3 grid{unsigned(tiles) * BLEND_SUBS, 1u, 1u}, block{unsigned(BLEND_THREADS), 1u, 1u};
-  StageTimer t_blend(ST_BLEND_FWD, st, 3);
+  StageTimer t_blend(ST_BLEND_FWD, st, 2);
   launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
   CG_LAUNCH_CHECK(s->debug, st);
   if (s->render_geo)
     launch_k(blend_fwd<true>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
-                                            out_map, im.final_T, im.n_contrib, im.tile_maxc);
+                                            out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, im.blk_cnt, im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
   else
     launch_k(blend_fwd<false>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
-                                             out_map, im.final_T, im.n_contrib, im.tile_maxc);
-  CG_LAUNCH_CHECK(s->debug, st);
-  // launch order of the backward CTAs, by the length of list each tile's backward will walk
-  launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, im.tile_maxc, im.tile_order_bwd);
+                                             out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, im.blk_cnt, im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
   CG_LAUNCH_CHECK(s->debug, st);
   return CG_OK;
 }
