@@ -34,14 +34,20 @@ constexpr int RING_WARPS = 4;     // per CTA; warps are independent
 #ifndef CG_RING_CTAS
 #define CG_RING_CTAS 6
 #endif
+#ifndef CG_RING_UNROLL
+#define CG_RING_UNROLL 1
+#endif
+constexpr int RING_UNROLL = CG_RING_UNROLL;   // steps per loop iteration
 constexpr int RING_NB = 2;        // blocks that may start within one epoch
 constexpr int RING_TSLOTS = 3 * RING_NB;
 constexpr uint32_t RING_POS_MASK = 0x0fffffffu;   // list position within the tile; bits 28-30 table slot, bit 31 first-of-block
 
 struct __align__(16) RingWarp {
-  float4 eA[2][32];               // staged elements of an epoch: x, y, conic a, conic b
-  float4 eB[2][32];               //                              conic c, opacity, colour, position|flags
-  float4 snap[32][3];             // sums of the element a lane just finished: S0..S3 | S4 S5 S7 - | A B C -
+  // (the quads are chosen so that every vector load / store of the per-step switch moves whole register quads:
+  //  no register is in two of them)
+  float4 eA[2][32];               // staged elements of an epoch: x, y, opacity, colour
+  float4 eB[2][32];               //                              conic a, b, c, position|flags
+  float4 snap[32][3];             // sums of the element a lane just finished: S0..S3 | S4 S5 S7 - | conic a b c -
   uint32_t gid[4][32];            // Gaussian index of the elements of an epoch (for the flush, two epochs later)
   float tT[RING_TSLOTS][32];      // pixel table of a block that starts in an epoch: final_T
   float tD[RING_TSLOTS][32];      //   dL/dpixel
@@ -52,6 +58,9 @@ struct __align__(16) RingWarp {
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
@@ -162,8 +171,9 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   int nc = 0;
   // ---- element state (this lane's current instance) ----
   float ex = 0.f, ey = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, eo = 0.f, col = 0.f;
-  uint32_t posw = RING_POS_MASK;
+  float poswf = __uint_as_float(RING_POS_MASK);   // position | flags word of the element, kept as the bits of eB.w
   float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, S4 = 0.f, S5 = 0.f, S7 = 0.f;
+  float spad = 0.f;   // fourth register of the {S4, S5, S7, -} quad the switch stores with one vector store
 
   // epoch bookkeeping: A = epoch m+1 (positions loaded, records not yet), B = epoch m+2 (being assigned)
   uint32_t posA = 0, rxA = 0, flagA = 0, nbA0 = 0xffffffffu, nbA1 = 0xffffffffu, validA = 0;
@@ -196,8 +206,13 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       if (E >= 0) {
         if (validA) {
           const Rec* r = rec + (size_t(rxA) + posA);
-          cp_async16(&rw.eA[E & 1][lane], &r->x);
-          cp_async16(&rw.eB[E & 1][lane], &r->cc);
+          float* ea = reinterpret_cast<float*>(&rw.eA[E & 1][lane]);
+          float* eb = reinterpret_cast<float*>(&rw.eB[E & 1][lane]);
+          cp_async8(ea, &r->x);        // x, y
+          cp_async4(ea + 2, &r->o);
+          cp_async4(ea + 3, &r->col);
+          cp_async8(eb, &r->ca);       // conic a, b
+          cp_async4(eb + 2, &r->cc);
           cp_async4(&rw.gid[E & 3][lane], point_list + (size_t(rxA) + posA));
           posw_pending = posA | flagA;
         } else {
@@ -240,9 +255,9 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     if (m < 0) continue;
 
     // ================= the 32 steps of period m =================
-    const float4* stA = &rw.eA[m & 1][lane];
-    const float4* stB = &rw.eB[m & 1][lane];
-#pragma unroll 1
+    const uint32_t stA_addr = smem_u32(&rw.eA[m & 1][lane]), stB_addr = smem_u32(&rw.eB[m & 1][lane]);
+    const uint32_t snap_addr = smem_u32(&rw.snap[lane][0]);
+#pragma unroll RING_UNROLL
     for (uint32_t u = 0; u < 32u; ++u) {
       T = __shfl_sync(FULL, T, src);
       Rp = __shfl_sync(FULL, Rp, src);
@@ -251,15 +266,27 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       pxf = __shfl_sync(FULL, pxf, src);
       pyf = __shfl_sync(FULL, pyf, src);
       if (has_bg) Tf = __shfl_sync(FULL, Tf, src);
-      if (lane == u) {
-        // pixel 0 arrives: the previous element has seen all 32 pixels
-        rw.snap[lane][0] = make_float4(S0, S1, S2, S3);
-        rw.snap[lane][1] = make_float4(S4, S5, S7, 0.f);
-        rw.snap[lane][2] = make_float4(ca, cb, cc, 0.f);
-        const float4 a = *stA, b = *stB;
-        ex = a.x; ey = a.y; ca = a.z; cb = a.w; cc = b.x; eo = b.y; col = b.z; posw = __float_as_uint(b.w);
-        S0 = S1 = S2 = S3 = S4 = S5 = S7 = 0.f;
+      {
+        // pixel 0 arrives at lane u: its previous element has seen all 32 pixels. One lane per step takes this
+        // path, so it is written as predicated vector accesses straight from / into the registers that hold the sums
+        // and the element (a branch plus compiler-chosen temporaries costs 8 more issue slots per step).
+        asm volatile(
+            "{\n\t.reg .pred sw;\n\t"
+            "setp.eq.u32 sw, %16, %17;\n\t"
+            "@sw st.shared.v4.f32 [%18], {%8, %9, %10, %11};\n\t"
+            "@sw st.shared.v4.f32 [%18+16], {%12, %13, %14, %15};\n\t"
+            "@sw st.shared.v4.f32 [%18+32], {%4, %5, %6, %7};\n\t"
+            "@sw ld.shared.v4.f32 {%0, %1, %2, %3}, [%19];\n\t"
+            "@sw ld.shared.v4.f32 {%4, %5, %6, %7}, [%20];\n\t"
+            "@sw mov.f32 %8, 0f00000000;\n\t@sw mov.f32 %9, 0f00000000;\n\t@sw mov.f32 %10, 0f00000000;\n\t"
+            "@sw mov.f32 %11, 0f00000000;\n\t@sw mov.f32 %12, 0f00000000;\n\t@sw mov.f32 %13, 0f00000000;\n\t"
+            "@sw mov.f32 %14, 0f00000000;\n\t}"
+            : "+f"(ex), "+f"(ey), "+f"(eo), "+f"(col), "+f"(ca), "+f"(cb), "+f"(cc), "+f"(poswf),
+              "+f"(S0), "+f"(S1), "+f"(S2), "+f"(S3), "+f"(S4), "+f"(S5), "+f"(S7), "+f"(spad)
+            : "r"(lane), "r"(u), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr)
+            : "memory");
       }
+      const uint32_t posw = __float_as_uint(poswf);
       if (posw & 0x80000000u) {
         // first element of its block (back to front): the arriving slot becomes pixel p of that block
         const uint32_t ts = (posw >> 28) & 7u, p = (u - lane) & 31u;
