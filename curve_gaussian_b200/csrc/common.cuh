@@ -302,7 +302,13 @@ inline uint32_t tile_key_bits(uint32_t n) {
 // and buffers are sized for (sync-free binning, cg_raster_fwd_capacity).
 template <typename K>
 int radix_sort_pairs(const SortBufs<K>& b, int64_t n, int end_bit, int* out_buf, bool debug, cudaStream_t stream,
-                     const uint32_t* d_n = nullptr);
+                     const uint32_t* d_n = nullptr, bool hist_ready = false);
+// A producer that writes b.keys[0] can fill the digit histograms itself: radix_sort_begin (clears b.hist and the
+// look-back state) -> producer adds, for every key and pass p, one count to b.hist[p * 256 + digit_p(key)]
+// (digit geometry from radix_sort_geometry) -> radix_sort_pairs(..., hist_ready = true) skips its histogram pass.
+void radix_sort_geometry(int end_bit, int key_bits, int* passes, int* bpp);
+template <typename K>
+int radix_sort_begin(const SortBufs<K>& b, int64_t n, int end_bit, cudaStream_t stream);
 // Which ping-pong buffer radix_sort_pairs leaves the result in (number of digit passes is ceil(end_bit / 8)).
 inline int radix_sort_result_buf(int end_bit) { int p = (end_bit + 7) / 8; return (p < 1 ? 1 : p) & 1; }
 

@@ -187,8 +187,14 @@ perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
 // work is balanced no matter how uneven the rects are.
 __global__ void __launch_bounds__(256)
 emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x, uint32_t* __restrict__ keys,
-          uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ nr_out) {
+          uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ nr_out, uint32_t* __restrict__ hist, int bpp) {
   pdl_wait();
+  // digit histograms of the tile sort that follows (two passes of bpp bits, see radix_sort_begin): counted here,
+  // while the keys are in registers anyway, instead of in a pass of their own over the R keys
+  __shared__ uint32_t s_hist[2][256];
+  s_hist[0][threadIdx.x] = 0;
+  s_hist[1][threadIdx.x] = 0;
+  const uint32_t dmask = (1u << bpp) - 1u;
   // capacity mode: report {R, R > capacity} to the caller's device counter; slots >= cap are dropped below
   // (the farthest instances, since emission is in depth order) and every later stage works on min(R, cap)
   if (nr_out && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -234,9 +240,17 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
     const uint32_t wdt = mxx - mnx;
     const uint32_t ry = local / wdt, rx = local - ry * wdt;
     if (base + o < cap) {
-      keys[base + o] = (mny + ry) * uint32_t(grid_x) + (mnx + rx);
+      const uint32_t key = (mny + ry) * uint32_t(grid_x) + (mnx + rx);
+      keys[base + o] = key;
       vals[base + o] = s_idx[lo];
+      atomicAdd(&s_hist[0][key & dmask], 1u);
+      atomicAdd(&s_hist[1][(key >> bpp) & dmask], 1u);
     }
+  }
+  __syncthreads();
+  if (hist && threadIdx.x <= dmask) {
+    if (s_hist[0][threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[0][threadIdx.x]);
+    if (s_hist[1][threadIdx.x]) atomicAdd(&hist[256 + threadIdx.x], s_hist[1][threadIdx.x]);
   }
 }
 
@@ -625,15 +639,19 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
     // the Gaussians were depth-sorted and their offsets scanned in that order by cg_raster_fwd_geom;
     // here: one (tile, Gaussian) pair per overlapped tile
     const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];
-    { StageTimer t_(ST_EMIT_KEYS, st, 1);
-    launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, gx, bs.is.keys[0], bs.is.vals[0],
-             uint32_t(R), nr_out); }
-    CG_LAUNCH_CHECK(s->debug, st);
-    // stable sort by tile only
+    // stable sort by tile only; emit_keys counts the digit histograms of its passes while it writes the keys
     int cur = 0;
     const int end_bit = int(tile_key_bits(uint32_t(tiles)));
+    int passes, bpp;
+    radix_sort_geometry(end_bit, 32, &passes, &bpp);
+    const bool fused_hist = passes <= 2;   // (up to 16 tile bits, i.e. any image below 4096 x 4096 pixels)
+    if (fused_hist) { rc = radix_sort_begin<uint32_t>(bs.is, R, end_bit, st); if (rc != CG_OK) return rc; }
+    { StageTimer t_(ST_EMIT_KEYS, st, 1);
+    launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, gx, bs.is.keys[0], bs.is.vals[0],
+             uint32_t(R), nr_out, fused_hist ? bs.is.hist : nullptr, bpp); }
+    CG_LAUNCH_CHECK(s->debug, st);
     { StageTimer t_(ST_SORT, st, 0);
-    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_n); }
+    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_n, fused_hist); }
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned((R + 255) / 256);
     { StageTimer t_(ST_GATHER, st, 1);

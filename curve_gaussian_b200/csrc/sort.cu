@@ -253,39 +253,66 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
 
 }  // namespace
 
+// Digit geometry of a sort of `end_bit` key bits: number of passes and (equal) bits per pass
+// (e.g. 13 tile bits -> 2 x 7 instead of 8 + 5: fewer bins per pass means longer runs per bin in the scatter and
+// fewer look-back chains).
+void radix_sort_geometry(int end_bit, int key_bits, int* passes, int* bpp) {
+  if (end_bit > key_bits) end_bit = key_bits;
+  int p = (end_bit + 7) / 8;
+  if (p < 1) p = 1;
+  *passes = p;
+  *bpp = end_bit <= 0 ? 1 : (end_bit + p - 1) / p;
+}
+
+// Clears the digit histograms, tickets and look-back words of a sort of n pairs. Called by radix_sort_pairs itself,
+// or - ahead of it - by a producer that fills b.hist while it writes the keys (emit_keys) and then passes
+// hist_ready = true.
+template <typename K>
+int radix_sort_begin(const SortBufs<K>& b, int64_t R, int end_bit, cudaStream_t stream) {
+  if (R <= 0) return CG_OK;
+  int passes, bpp;
+  radix_sort_geometry(end_bit, int(8 * sizeof(K)), &passes, &bpp);
+  const int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
+  // hist, ticket and status are carved back to back: one memset covers all three
+  CG_CUDA(cudaMemsetAsync(b.hist, 0,
+                          size_t(reinterpret_cast<char*>(b.status + size_t(passes) * ntiles * 256) -
+                                 reinterpret_cast<char*>(b.hist)), stream));
+  return CG_OK;
+}
+
 template <typename K>
 int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf, bool debug, cudaStream_t stream,
-                     const uint32_t* d_n) {
+                     const uint32_t* d_n, bool hist_ready) {
   *out_buf = 0;
   if (R <= 0) return CG_OK;
   if (R >= (int64_t(1) << FLAG_SHIFT)) {
     set_error("radix sort: %lld pairs exceed the 2^30 look-back word", (long long)R);
     return CG_ERR_CAPACITY;
   }
-  if (end_bit > int(8 * sizeof(K))) end_bit = int(8 * sizeof(K));
-  int passes = (end_bit + 7) / 8;
-  if (passes < 1) passes = 1;
-  // equal digit widths (e.g. 13 tile bits -> 2 x 7 instead of 8 + 5): fewer bins per pass means
-  // longer runs per bin in the scatter and fewer look-back chains
-  const int bpp = end_bit <= 0 ? 1 : (end_bit + passes - 1) / passes;
+  int passes, bpp;
+  radix_sort_geometry(end_bit, int(8 * sizeof(K)), &passes, &bpp);
   const uint32_t dmask = (1u << bpp) - 1u;
   const int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  // (per device: a process that drives several GPUs sets the attribute on each of them)
+  static thread_local bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CUDA(cudaGetDevice(&dev));
+  CG_ARG(dev >= 0 && dev < 64, "device ordinal");
+  if (!attr_set[dev]) {
     CG_CUDA(cudaFuncSetAttribute(sort_onesweep_pass<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(sizeof(SortSmem<K>))));
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  // hist, ticket and status are carved back to back: one memset covers all three
-  CG_CUDA(cudaMemsetAsync(b.hist, 0,
-                          size_t(reinterpret_cast<char*>(b.status + size_t(passes) * ntiles * 256) -
-                                 reinterpret_cast<char*>(b.hist)), stream));
-
-  int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
-  count_launches(2 + passes);
-  launch_k(sort_histogram<K>, dim3(hist_blocks), dim3(256), 0, stream, b.keys[0], R, d_n, passes, bpp, b.hist);
-  CG_LAUNCH_CHECK(debug, stream);
+  if (!hist_ready) {
+    int rc = radix_sort_begin<K>(b, R, end_bit, stream);
+    if (rc != CG_OK) return rc;
+    int hist_blocks = int(ntiles < 148 * 8 ? ntiles : 148 * 8);
+    count_launches(1);
+    launch_k(sort_histogram<K>, dim3(hist_blocks), dim3(256), 0, stream, b.keys[0], R, d_n, passes, bpp, b.hist);
+    CG_LAUNCH_CHECK(debug, stream);
+  }
+  count_launches(1 + passes);
   launch_k(sort_scan_bins, dim3(passes), dim3(256), 0, stream, b.hist);
   CG_LAUNCH_CHECK(debug, stream);
 
@@ -300,7 +327,9 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
   return CG_OK;
 }
 
-template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*);
-template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*);
+template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*, bool);
+template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*, bool);
+template int radix_sort_begin<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, cudaStream_t);
+template int radix_sort_begin<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, cudaStream_t);
 
 }  // namespace cg

@@ -102,17 +102,21 @@ class CapacityBinning:
         self.max_seen: dict = {}      # (P, W, H) -> largest R observed
         self._pending: list = []      # (key, pinned int32[2], event, capacity used)
         self._free: list = []
-        self._static: dict = {}       # key -> pinned int32[2] refreshed by graph replays
+        self._static: dict = {}       # key -> pinned int32[3] refreshed by graph replays
+        self._sticky: dict = {}       # key -> device int32[2]: running max of {R, overflow} over the graph replays
+                                      # since the last check() (a later, smaller view must not hide an overflow)
         self.overflows = 0
 
     def _round(self, R: int) -> int:
         g = self.granule
         return max(g, (int(R * self.headroom) + g - 1) // g * g)
 
-    def learn(self, key, R: int) -> None:
+    def learn(self, key, R: int, device=None) -> None:
         if key not in self._static and not _capturing():
             # (pinned allocations are not allowed while a capture is open, so the slot exists beforehand)
             self._static[key] = _pinned_i32(3)
+        if device is not None and key not in self._sticky and not _capturing():
+            self._sticky[key] = torch.zeros(2, dtype=torch.int32, device=device)
         if R > self.max_seen.get(key, -1):
             self.max_seen[key] = int(R)
             if self._round(R) > self.caps.get(key, 0):
@@ -127,7 +131,12 @@ class CapacityBinning:
             # inside a CUDA graph: a fixed pinned slot, rewritten by every replay, read by check()
             slot = self._static[key]
             slot[2] = cap
-            slot[:2].copy_(counter, non_blocking=True)
+            sticky = self._sticky.get(key)
+            if sticky is None:
+                raise _lib.CurveGSError(f"no overflow accumulator for (P, W, H) = {key}: run the step once outside "
+                                        "the CUDA graph capture first")
+            torch.maximum(sticky, counter, out=sticky)    # part of the graph: every replay folds its {R, overflow} in
+            slot[:2].copy_(sticky, non_blocking=True)
             return
         if len(self._pending) >= 64:
             self.poll()           # a caller that never polls: keep the queue bounded (may raise for an earlier step)
@@ -168,6 +177,8 @@ class CapacityBinning:
         for key, slot in self._static.items():
             R, over, cap = int(slot[0]), int(slot[1]), int(slot[2])
             slot[1] = 0   # reported once
+            if key in self._sticky:
+                self._sticky[key].zero_()   # stream-ordered behind the replays the caller synchronised on
             if self._account(key, R, over, cap):
                 raise CapacityOverflow(f"{R} tile-instances exceeded the captured binning capacity {cap} for "
                                        f"(P, W, H) = {key}; re-capture the step (the capacity was raised)")
@@ -245,6 +256,8 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
         raise _lib.CurveGSError("colors_precomp is required (the SH path is not part of the curve pipeline)")
 
     key = (P, W, H)
+    if _policy is not None and key not in _policy._sticky and not _capturing():
+        _policy._sticky[key] = torch.zeros(2, dtype=torch.int32, device=dev)
     if capacity is None and _policy is not None:
         capacity = _policy.capacity(key)
         if capacity is None and _capturing():
@@ -285,7 +298,7 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
     rasterize_forward_raw.last_R = R
     rasterize_forward_raw.last_counter = None
     if _policy is not None:
-        _policy.learn(key, R)
+        _policy.learn(key, R, dev)
     return R, color, radii, geom, bin_keep, img, invdepth, out_all_map
 
 

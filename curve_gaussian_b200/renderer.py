@@ -68,11 +68,15 @@ _ONES = {}
 
 def _ones(P: int, dev) -> torch.Tensor:
     """(P,1) ones (the single colour channel, gaussian_renderer/__init__.py:97), cached per size and device."""
+    # Entries are never evicted while they may be baked into a captured CUDA graph as `colors_precomp` (a render of
+    # another model size between two replays must not hand that memory back to the allocator); the cache is
+    # bounded instead: past 16 shapes new ones are simply not cached.
     key = (int(P), str(dev))
     t = _ONES.get(key)
     if t is None:
-        _ONES.clear()
-        t = _ONES[key] = torch.ones(P, 1, device=dev)
+        t = torch.ones(P, 1, device=dev)
+        if len(_ONES) < 16:
+            _ONES[key] = t
     return t
 
 

@@ -131,7 +131,9 @@ class TrainLoop:
             terms["mask"] = opt.lambda_mask * torch.sigmoid(m._mask).mean()
         terms["opacity"] = opt.opacity_loss_weight * opacity_regulariser(m.get_opacity, pkg["radii"] > 0)
         if opt.lambda_curve_smo > 0:
-            terms["curve_smo"] = opt.lambda_curve_smo * curve_smoothness(m._rotation, m.n_gaussians)
+            # train.py:119 adds it only `if visibility_filter.sum() > 0`: the same gate, kept on the device
+            gate = (pkg["radii"] > 0).any().to(torch.float32)
+            terms["curve_smo"] = opt.lambda_curve_smo * gate * curve_smoothness(m._rotation, m.n_gaussians)
         if opt.lambda_width > 0:
             terms["width"] = opt.lambda_width * width_regulariser(m.get_curve_width)
         if opt.lambda_points_conn > 0 and iteration > opt.conn_from_iter:

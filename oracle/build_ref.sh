@@ -32,3 +32,16 @@ for sub in diff-cur-rasterization fused-ssim simple-knn; do
   cp "$built" "$OUT/$so"
   echo "built $so"
 done
+
+# The reference's pure-Python side of the hot path (model sampling, render(), losses, the two extension wrappers),
+# staged UNMODIFIED into the git-ignored oracle/_ref/py/ so that oracle/ref_step.py can drive the reference's real
+# train.py step on the GPU box (where /root/reference does not exist). Nothing here enters the repository history.
+PY=$OUT/py
+mkdir -p "$PY/scene" "$PY/utils" "$PY/gaussian_renderer" "$PY/diff_cur_rasterization" "$PY/fused_ssim"
+cp "$REF/scene/gaussian_curve_model.py" "$REF/scene/gaussian_model.py" "$PY/scene/"
+cp "$REF/utils/general_utils.py" "$REF/utils/graphics_utils.py" "$REF/utils/sh_utils.py" "$REF/utils/system_utils.py" \
+   "$REF/utils/loss_utils.py" "$PY/utils/"
+cp "$REF/gaussian_renderer/__init__.py" "$PY/gaussian_renderer/__init__.py"
+cp "$REF/submodules/diff-cur-rasterization/diff_cur_rasterization/__init__.py" "$PY/diff_cur_rasterization/__init__.py"
+cp "$REF/submodules/fused-ssim/fused_ssim/__init__.py" "$PY/fused_ssim/__init__.py"
+echo "staged reference python under $PY"

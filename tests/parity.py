@@ -1,0 +1,82 @@
+"""Parity metrics shared by the GPU tests, and a recorder for the numbers they measure.
+
+Two figures per comparison:
+  max_rel  max |a - b| / max |b|                      - BASELINE.json's "max-rel"; the bar is 1e-5
+  rel_err  max |a - b| / (|b| + 1e-5 max|b|)          - SURVEY.md section 7: every element against its own
+           magnitude, floored five decades below the largest (sees a 100 % error on an element 1e5 x smaller than
+           the largest, which max_rel cannot)
+Gradients of this path are sums of fp32 atomics in the reference, which therefore does not reproduce itself: two
+runs of the reference on identical inputs differ by 1e-7..6e-7 in max_rel and by 1e-5..3e-3 in rel_err (elements that
+are the small difference of large terms carry the summation noise of the large terms). So:
+  * ASSERTED: max_rel <= max(tol, NOISE_FACTOR x the reference's own run-to-run max_rel), and - so that a systematic
+    error confined to small elements cannot hide - the share of elements whose own relative error exceeds 1e-4 must
+    stay below max(1e-3, 5 x the same share between two reference runs);
+  * RECORDED next to it: rel_err and the reference's run-to-run rel_err, in gpurun_out/parity/*.jsonl (copied to
+    profiles/parity_r02.json).
+"""
+import json
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NOISE_FACTOR = 3.0
+
+
+def rel_err(a, b, floor=1e-5):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    if a.numel() == 0:
+        return 0.0
+    mx = b.abs().max().item()
+    if mx == 0:
+        return (a - b).abs().max().item()
+    return ((a - b).abs() / (b.abs() + floor * mx)).max().item()
+
+
+def max_rel(a, b):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    if a.numel() == 0:
+        return 0.0
+    mx = b.abs().max().item()
+    return (a - b).abs().max().item() / mx if mx else (a - b).abs().max().item()
+
+
+def record(file, **fields):
+    out = os.path.join(ROOT, "gpurun_out", "parity")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, file + ".jsonl"), "a") as f:
+            f.write(json.dumps(fields) + "\n")
+    except OSError:
+        pass
+
+
+def frac_beyond(a, b, thresh=1e-4, floor=1e-5):
+    """Share of elements with |a - b| / (|b| + floor max|b|) > thresh."""
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    if a.numel() == 0:
+        return 0.0
+    mx = b.abs().max().item()
+    if mx == 0:
+        return float(((a - b).abs() > 0).double().mean())
+    return float((((a - b).abs() / (b.abs() + floor * mx)) > thresh).double().mean())
+
+
+def check(file, case, name, ours, ref, ref_again=(), tol=1e-5):
+    """Assert ours == ref as described in the module docstring; record every figure."""
+    err, err_el = max_rel(ours, ref), rel_err(ours, ref)
+    noise = max([max_rel(r, ref) for r in ref_again], default=0.0)
+    noise_el = max([rel_err(r, ref) for r in ref_again], default=0.0)
+    fb, fb_noise = frac_beyond(ours, ref), max([frac_beyond(r, ref) for r in ref_again], default=0.0)
+    record(file, case=case, quantity=name, max_rel=err, ref_self_noise_max_rel=noise, rel_err=err_el,
+           ref_self_noise=noise_el, share_elements_beyond_1e4=fb, ref_self_share_beyond_1e4=fb_noise, tol=tol,
+           bit_identical=bool(torch.equal(torch.as_tensor(ours).cpu(), torch.as_tensor(ref).cpu())))
+    assert err <= max(tol, NOISE_FACTOR * noise), (
+        f"{case}/{name}: max-rel err {err:.3e} > max({tol:g}, {NOISE_FACTOR:g} x reference self-noise {noise:.3e})")
+    assert fb <= max(1e-3, 5 * fb_noise), (
+        f"{case}/{name}: {fb:.2e} of the elements are off by more than 1e-4 of their own magnitude "
+        f"(between two reference runs: {fb_noise:.2e})")
+    return err, noise

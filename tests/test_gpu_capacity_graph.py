@@ -213,3 +213,39 @@ def test_graphed_step_recaptures_after_overflow(cuda_dev):
     torch.cuda.synchronize()
     assert gs.verify()
     assert torch.equal(img, refs[hi])
+
+
+def test_overflow_is_sticky_across_replays(cuda_dev):
+    """An overflowing replay followed by a cheap one must still be reported: the {R, overflow} slot is a running
+    maximum over the replays since the last check(), not the last replay's value."""
+    dev = cuda_dev
+    B, n, W, H = 150, 16, 192, 128
+    cp, width, opl, isb = synth.random_curves(B, seed=21)
+    width = width + 0.6
+    cams = [c.to(dev) for c in synth.random_cameras(8, W, H, seed=22)]
+    bg = torch.zeros(3, device=dev)
+    model = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb)
+    model.prepare_scaling_rot()
+    Rs = []
+    with torch.no_grad():
+        for c in cams:
+            render(c, model, Pipe(), bg)
+            Rs.append(rz.rasterize_forward_raw.last_R)
+    lo, hi = Rs.index(min(Rs)), Rs.index(max(Rs))
+    scam = StaticCamera(cams[lo])
+
+    def step():
+        model.prepare_scaling_rot()
+        with torch.no_grad():
+            return render(scam, model, Pipe(), bg)["render_raw"] * 1.0
+
+    pol = rz.CapacityBinning(headroom=1.0, granule=64)
+    gs = GraphedStep(step, policy=pol).capture()
+    gs.replay()
+    scam.load(cams[hi])      # overflows ...
+    gs.replay()
+    scam.load(cams[lo])      # ... and the next replay fits again
+    gs.replay()
+    torch.cuda.synchronize()
+    assert not gs.verify(), "the overflow of the middle replay was lost"
+    assert pol.max_seen[(B * n, W, H)] >= Rs[hi]

@@ -48,6 +48,34 @@ def test_sampling_matches_reference_golden(cuda_dev, path):
     assert rel(width.grad, w2.grad) <= 2e-5
 
 
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_sampling_and_activation_gradients_match_reference_golden(cuda_dev, path):
+    """dL/d{control points, width, opacity, mask} of the CUDA sampling + activation ops against the gradients the
+    REFERENCE's own autograd produced for the same weighted sum of all seven per-Gaussian outputs
+    (tests/golden/make_sampling_golden.py: g_curve_points, g_width, g_opacity, g_mask), <= 1e-5."""
+    from curve_gaussian_b200.activation import curve_activate
+    from tests import parity
+    z = np.load(path)
+    d = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim}
+    n, use_mask, dev = int(z["n"]), bool(z["use_mask"]), cuda_dev
+    leaf = lambda k: d[k].to(dev).requires_grad_(True)
+    cp, width, opl, mask = leaf("curve_points"), leaf("width"), leaf("opacity_logit"), leaf("mask_logit")
+    xyz, rot, scal = sampling.sample_curves(cp, width, d["is_bezier"].to(dev), sampling.sample_t(n, dev))
+    rot_n, opacity, scales, all_map = curve_activate(xyz, rot, scal, opl, mask, n, d["cam_center"].to(dev),
+                                                     d["world_view"].to(dev), use_mask, 0.01)
+    outs = (xyz, rot, scal, opacity, rot_n, scales, all_map[:, :3])
+    keys = ("xyz", "rot", "scal", "opacity", "rot_n", "scales", "local")
+    for o, k, ref in zip(outs, keys, ("xyz", "rotation", "scaling", "opacity", "rot_normalized", "scales_masked", "local_axis")):
+        assert rel(o, d[ref]) <= 1e-5, ref
+    sum((o * d["w_" + k].to(dev)).sum() for o, k in zip(outs, keys)).backward()
+    case = os.path.basename(path)
+    for name, p_ in (("g_curve_points", cp), ("g_width", width), ("g_opacity", opl), ("g_mask", mask)):
+        g = p_.grad if p_.grad is not None else torch.zeros_like(p_)
+        e = rel(g, d[name]) if d[name].abs().max() > 0 else float(g.abs().max())
+        parity.record("sampling_vs_reference_golden", case=case, quantity=name, max_rel=e, rel_err=parity.rel_err(g.cpu(), d[name]), tol=1e-5)
+        assert e <= 1e-5, (name, e)
+
+
 @pytest.mark.parametrize("B,n,lines", [(500, 12, 0.0), (300, 100, 0.3), (4000, 33, 0.5)])
 def test_sampling_matches_torch_restatement(cuda_dev, B, n, lines):
     cp0, w0, _, isb = synth.random_curves(B, seed=B, line_fraction=lines)

@@ -141,3 +141,19 @@ def test_masked_mean_regularisers_equal_the_reference_formulations():
     (gb,) = torch.autograd.grad(ref, logw)
     assert torch.allclose(ours, ref, rtol=1e-12) and torch.allclose(ga, gb, rtol=1e-10, atol=1e-18)
     assert float(width_regulariser(torch.full((5, 1), 1e-3))) == 0.0
+
+
+def test_balanced_view_partition_equal_sizes_and_near_equal_cost():
+    import random
+    from curve_gaussian_b200.parallel import balanced_view_partition
+    rng = random.Random(3)
+    for world, per in ((2, 256), (4, 128), (8, 64), (8, 1), (1, 7)):
+        costs = [rng.uniform(6.0e6, 1.0e7) for _ in range(world * per)]
+        parts = balanced_view_partition(costs, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))      # every view exactly once
+        assert all(len(p) == per for p in parts)
+        tot = [sum(costs[i] for i in p) for p in parts]
+        assert max(tot) - min(tot) <= max(costs) - min(costs) + 1e-6                # within one view's cost spread
+    import pytest
+    with pytest.raises(ValueError):
+        balanced_view_partition([1.0, 2.0, 3.0], 2)
