@@ -365,8 +365,6 @@ def run_ours(a):
         # depth sort of the P Gaussians (histogram read + 4 passes of 8-byte pairs r+w) and tile sort of the
         # R instances (histogram read + 2 passes of 8-byte pairs r+w); radix_sort is timed per launch, so use R's
         "radix_sort": (4 + 2 * 16) * (R or 0),
-        # read (tile, id) 8 + gathered attributes 48, write record 48 + id 4 + cull box 16
-        "gather_records": (8 + 48 + 68) * (R or 0),
         "preprocess_fwd": (44 + 36) * P,
         "preprocess_bwd": (76 + 40) * P,
     }

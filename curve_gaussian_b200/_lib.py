@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CURVEGS_LIB selects another build of the same library (A/B timing of kernel variants, see build.build_variant)
 LIB_PATH = os.environ.get("CURVEGS_LIB") or os.path.join(_HERE, "libcurvegs.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class RasterSettings(C.Structure):
@@ -55,8 +55,8 @@ SIGNATURES = {
     "cg_raster_bin_keep_bytes": (_sz, [_i64]),
     "cg_raster_bin_scratch_bytes": (_sz, [_i64, _i64]),
     "cg_raster_bwd_scratch_bytes": (_sz, [_i64]),
-    "cg_raster_fwd_geom": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
-    "cg_raster_fwd_blend": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_raster_fwd_geom": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
+    "cg_raster_fwd_blend": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_raster_fwd_capacity": (C.c_int, [_SP, _i64, _i64] + [_vp] * 9 + [_sz] + [_vp] * 8),
     "cg_set_pdl": (None, [C.c_int]),
     "cg_raster_bwd": (C.c_int, [_SP, _i64, _i64] + [_vp] * 22),

@@ -64,15 +64,14 @@ static void drain_profile() {
   g_pending.clear();
 }
 static const char* kStageNames[ST_COUNT] = {"sample_fwd", "preprocess_fwd", "scan", "emit_keys", "radix_sort",
-                                            "tile_ranges", "gather_records", "blend_fwd", "blend_bwd",
+                                            "tile_ranges", "gather_records(unused)", "blend_fwd", "blend_bwd",
                                             "preprocess_bwd", "sample_bwd", "ssim_fwd", "ssim_bwd", "knn",
                                             "activate_fwd", "activate_bwd", "loss_fwd", "loss_bwd"};
 
 int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
-                    const float* scales, const float* rotations, const float* cov3D_precomp,
-                    int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st);
-int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
-                     void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
+                    const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
+                    const float* all_map, int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st);
+int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
                      float* out_map, uint32_t* nr_out, cudaStream_t st);
 int launch_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* means3D, const float* opacities,
                const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
@@ -98,7 +97,7 @@ using namespace cg;
 
 extern "C" {
 
-int cg_abi_version(void) { return 5; }
+int cg_abi_version(void) { return 6; }
 void cg_set_pdl(int on) { g_use_pdl = on ? 1 : 0; }
 uint64_t cg_launch_count(void) { return g_launches.load(); }
 void cg_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
@@ -140,29 +139,31 @@ size_t cg_raster_bin_scratch_bytes(int64_t P, int64_t R) {
 size_t cg_raster_bwd_scratch_bytes(int64_t P) { return size_t(P < 1 ? 1 : P) * 8 * sizeof(float); }
 
 int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
-                       const float* scales, const float* rotations, const float* cov3D_precomp, int32_t* radii,
-                       void* geom, size_t geom_bytes, int64_t* num_rendered, void* stream) {
+                       const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
+                       const float* all_map, int32_t* radii, void* geom, size_t geom_bytes, int64_t* num_rendered,
+                       void* stream) {
   int rc = check_settings(s);
   if (rc) return rc;
   CG_ARG(num_rendered != nullptr, "num_rendered");
   *num_rendered = 0;
   if (P == 0) return CG_OK;
   CG_ARG(P > 0 && P < (int64_t(1) << 31), "P");
-  CG_ARG(means3D && opacities && radii && geom, "means3D/opacities/radii/geom");
+  CG_ARG(means3D && opacities && radii && geom && colors, "means3D/opacities/colors/radii/geom");
   CG_ARG((scales && rotations && !cov3D_precomp) || (!scales && !rotations && cov3D_precomp),
          "exactly one of scale/rotation pair or precomputed 3D covariance");
+  CG_ARG(!s->render_geo || all_map, "all_map required with render_geo");
+  CG_ARG(!all_map || (reinterpret_cast<uintptr_t>(all_map) & 15u) == 0, "all_map must be 16-byte aligned");
   if (geom_bytes < cg_raster_geom_bytes(P)) {
     set_error("geom buffer too small: %zu < %zu", geom_bytes, cg_raster_geom_bytes(P));
     return CG_ERR_CAPACITY;
   }
   CG_ARG((reinterpret_cast<uintptr_t>(geom) & 127u) == 0, "geom must be 128-byte aligned");
-  return launch_fwd_geom(s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, geom, num_rendered,
-                         reinterpret_cast<cudaStream_t>(stream));
+  return launch_fwd_geom(s, P, means3D, opacities, scales, rotations, cov3D_precomp, colors, all_map, radii, geom,
+                         num_rendered, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
-                        void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color,
-                        float* out_invdepth, float* out_all_map, void* stream) {
+int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* geom, void* img, void* bin_keep,
+                        void* bin_scratch, float* out_color, float* out_invdepth, float* out_all_map, void* stream) {
   int rc = check_settings(s);
   if (rc) return rc;
   CG_ARG(P >= 0 && R >= 0, "P/R");
@@ -170,13 +171,11 @@ int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const
   CG_ARG(!s->render_geo || out_all_map, "out_all_map required with render_geo");
   CG_ARG((reinterpret_cast<uintptr_t>(img) & 127u) == 0, "img must be 128-byte aligned");
   if (R > 0) {
-    CG_ARG(geom && bin_keep && bin_scratch && colors, "geom/bin_keep/bin_scratch/colors");
-    CG_ARG(!s->render_geo || all_map, "all_map required with render_geo");
+    CG_ARG(geom && bin_keep && bin_scratch, "geom/bin_keep/bin_scratch");
     CG_ARG((reinterpret_cast<uintptr_t>(bin_keep) & 127u) == 0 && (reinterpret_cast<uintptr_t>(bin_scratch) & 127u) == 0,
            "bin buffers must be 128-byte aligned");
-    CG_ARG(!all_map || (reinterpret_cast<uintptr_t>(all_map) & 15u) == 0, "all_map must be 16-byte aligned");
   }
-  return launch_fwd_blend(s, P, R, colors, all_map, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
+  return launch_fwd_blend(s, P, R, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
                           out_all_map, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -204,9 +203,9 @@ int cg_raster_fwd_capacity(const cg_raster_settings* s, int64_t P, int64_t R_cap
            reinterpret_cast<uintptr_t>(bin_scratch)) & 127u) == 0, "state buffers must be 128-byte aligned");
   CG_ARG(!all_map || (reinterpret_cast<uintptr_t>(all_map) & 15u) == 0, "all_map must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  rc = launch_fwd_geom(s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, geom, nullptr, st);
+  rc = launch_fwd_geom(s, P, means3D, opacities, scales, rotations, cov3D_precomp, colors, all_map, radii, geom, nullptr, st);
   if (rc) return rc;
-  return launch_fwd_blend(s, P, R_cap, colors, all_map, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
+  return launch_fwd_blend(s, P, R_cap, geom, img, bin_keep, bin_scratch, out_color, out_invdepth,
                           out_all_map, num_rendered_dev, st);
 }
 
@@ -259,9 +258,14 @@ int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
     case 1: CG_ARG(bin_keep != nullptr, "bin_keep"); src = bk.point_list; bytes = size_t(R) * 4; break;
     case 2: src = im.ranges; bytes = tiles * 8; break;
     case 3: src = g.tiles; bytes = size_t(P) * 4; break;
-    case 4: src = g.xy; bytes = size_t(P) * 8; break;
+    case 4:   // means2D (x, y): strided out of the per-Gaussian records
+      CG_CUDA(cudaMemcpy2DAsync(dst, 8, &g.grec[0].x, sizeof(Rec), 8, size_t(P), cudaMemcpyDeviceToDevice, st));
+      return CG_OK;
     case 5: src = g.depth; bytes = size_t(P) * 4; break;
-    case 6: src = g.conic_o; bytes = size_t(P) * 16; break;
+    case 6:   // conic_opacity (conic xx, xy, yy, opacity)
+      CG_CUDA(cudaMemcpy2DAsync(dst, 16, &g.grec[0].ca, sizeof(Rec), 12, size_t(P), cudaMemcpyDeviceToDevice, st));
+      CG_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(dst) + 12, 16, &g.grec[0].o, sizeof(Rec), 4, size_t(P), cudaMemcpyDeviceToDevice, st));
+      return CG_OK;
     case 7: src = im.n_contrib; bytes = size_t(W) * H * 4; break;
     case 8: src = im.final_T; bytes = size_t(W) * H * 4; break;
     default: set_error("debug_fetch: unknown selector %d", which); return CG_ERR_ARG;

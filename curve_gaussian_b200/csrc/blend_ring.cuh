@@ -15,7 +15,7 @@
 // switches to its next element at step 32m+i, when pixel 0 arrives; an element flagged as the first of its
 // block re-initialises every pixel slot that reaches it from that block's pixel table. Everything that is
 // not per step happens at the epoch boundaries, for all lanes at once: candidate positions are loaded two
-// epochs ahead, the 32-byte records one epoch ahead (cp.async straight into the lane's staging slot), the
+// epochs ahead, the 32-byte records one epoch ahead (cp.async from the per-Gaussian table straight into the lane's staging slot), the
 // sums of finished instances are flushed one epoch late.
 //
 // Gradient sums kept per instance (q = o * G * dL/dalpha, d = mean2D - pixel):
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, CG_RING_CTAS)
 blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cls_count,
                const uint32_t* __restrict__ cls_list, uint32_t nblocks, uint32_t* __restrict__ work,
                const uint32_t* __restrict__ blk_cnt, int grid_x,
-               const Rec* __restrict__ rec, const uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cand,
+               const Rec* __restrict__ grec, const uint32_t* __restrict__ cand, const uint32_t* __restrict__ cand_id,
                int W, int H, float ddelx_dx, float ddely_dy, const float* __restrict__ bg,
                const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                const float* __restrict__ dL_dpix, float* __restrict__ acc) {
@@ -129,15 +129,15 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   };
   if (lane < 4) load_meta(int(lane));
   uint32_t j_next = 0;            // next queue entry to start
-  uint32_t cb_rem = 0, cb_base = 0, cb_rx = 0;   // block being consumed: entries left (taken from the end), list base, range start
+  uint32_t cb_rem = 0, cb_base = 0;   // block being consumed: entries left (taken from the end), list base
 
   // assignment of epoch E: which list entry each lane takes; a_addr = index into cand (or ~0), a_flag = first|slot bits.
   // At most RING_NB blocks start per epoch (they need a pixel table each); empty blocks are skipped. An epoch
   // without any element therefore means that the warp has run out of blocks.
-  auto assign = [&](int E, uint32_t& a_addr, uint32_t& a_rx, uint32_t& a_flag, uint32_t& nb0, uint32_t& nb1) -> uint32_t {
-    a_addr = 0xffffffffu; a_rx = 0; a_flag = 0; nb0 = nb1 = 0xffffffffu;
+  auto assign = [&](int E, uint32_t& a_addr, uint32_t& a_flag, uint32_t& nb0, uint32_t& nb1) -> uint32_t {
+    a_addr = 0xffffffffu; a_flag = 0; nb0 = nb1 = 0xffffffffu;
     uint32_t taken = min(cb_rem, 32u);
-    if (lane < taken) { a_addr = cb_base + (cb_rem - 1u - lane); a_rx = cb_rx; }
+    if (lane < taken) a_addr = cb_base + (cb_rem - 1u - lane);
     cb_rem -= taken;
     int started = 0;
     while (taken < 32u && started < RING_NB) {
@@ -153,12 +153,11 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
           const uint32_t n = min(cnt, 32u - taken);
           if (lane >= taken && lane < taken + n) {
             a_addr = base + (cnt - 1u - (lane - taken));
-            a_rx = rx;
             if (lane == taken) a_flag = 0x80000000u | (uint32_t((E % 3) * RING_NB + started) << 28);
           }
           if (started == 0) nb0 = bid; else nb1 = bid;
           ++started;
-          cb_rem = cnt - n; cb_base = base; cb_rx = rx;
+          cb_rem = cnt - n; cb_base = base;
           taken += n;
         }
       }
@@ -176,7 +175,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   float spad = 0.f;   // fourth register of the {S4, S5, S7, -} quad the switch stores with one vector store
 
   // epoch bookkeeping: A = epoch m+1 (positions loaded, records not yet), B = epoch m+2 (being assigned)
-  uint32_t posA = 0, rxA = 0, flagA = 0, nbA0 = 0xffffffffu, nbA1 = 0xffffffffu, validA = 0;
+  uint32_t posA = 0, idA = 0, flagA = 0, nbA0 = 0xffffffffu, nbA1 = 0xffffffffu, validA = 0;
   uint32_t posw_pending = RING_POS_MASK;     // position|flags word of this lane's element of the next epoch
   uint32_t real_m2 = 0, real_m1 = 0, real_0 = 0, real_p1 = 0;   // real elements of epochs m-2, m-1, m, m+1
 
@@ -205,15 +204,10 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       const int E = m + 1;
       if (E >= 0) {
         if (validA) {
-          const Rec* r = rec + (size_t(rxA) + posA);
-          float* ea = reinterpret_cast<float*>(&rw.eA[E & 1][lane]);
-          float* eb = reinterpret_cast<float*>(&rw.eB[E & 1][lane]);
-          cp_async8(ea, &r->x);        // x, y
-          cp_async4(ea + 2, &r->o);
-          cp_async4(ea + 3, &r->col);
-          cp_async8(eb, &r->ca);       // conic a, b
-          cp_async4(eb + 2, &r->cc);
-          cp_async4(&rw.gid[E & 3][lane], point_list + (size_t(rxA) + posA));
+          const Rec* r = grec + idA;                    // the per-Gaussian record, gathered by index (L2-resident table)
+          cp_async16(&rw.eA[E & 1][lane], &r->x);       // x, y, opacity, colour
+          cp_async16(&rw.eB[E & 1][lane], &r->ca);      // conic a, b, c (+ 1/depth, overwritten by the position word)
+          rw.gid[E & 3][lane] = idA;
           posw_pending = posA | flagA;
         } else {
           rw.eA[E & 1][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -245,11 +239,12 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     }
     {
       // assignment of epoch m+2 and its candidate positions (consumed at the next boundary)
-      uint32_t a_addr, a_rx, a_flag, nb0, nb1;
-      const uint32_t real_p2 = assign(m + 2, a_addr, a_rx, a_flag, nb0, nb1);
+      uint32_t a_addr, a_flag, nb0, nb1;
+      const uint32_t real_p2 = assign(m + 2, a_addr, a_flag, nb0, nb1);
       validA = a_addr != 0xffffffffu;
       posA = validA ? cand[a_addr] : 0u;
-      rxA = a_rx; flagA = a_flag; nbA0 = nb0; nbA1 = nb1;
+      idA = validA ? cand_id[a_addr] : 0u;
+      flagA = a_flag; nbA0 = nb0; nbA1 = nb1;
       real_m2 = real_m1; real_m1 = real_0; real_0 = real_p1; real_p1 = real_p2;
     }
     if (m < 0) continue;

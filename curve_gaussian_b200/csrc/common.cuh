@@ -109,13 +109,17 @@ struct Carver {
   }
 };
 
-// One sorted tile-instance, staged into shared memory by a bulk async copy.
-// 48 bytes = 3 x 16B, so any run of records is a legal cp.async.bulk span.
+// One projected Gaussian as the blend kernels consume it (GeomState::grec, written once per Gaussian by
+// preprocess_fwd). There is no per-tile-instance copy of it: the blend kernels gather the records of a batch of
+// their tile's sorted list by Gaussian index (three 16-byte async copies per record, from a table that stays in
+// L2: 48 B x P), instead of streaming 48 B x R materialised, sorted records of which the forward's early
+// termination leaves three quarters unread. The quads are laid out for the ring backward, whose per-step element
+// switch moves whole register quads (blend_ring.cuh).
 struct __align__(16) Rec {
+  float ca, cb, cc;    // conic xx, xy, yy          (geomState.conic_opacity.xyz)
+  float invd;          // 1 / view-space depth
   float x, y;          // pixel-space mean           (geomState.means2D)
-  float ca, cb;        // conic xx, xy
-  float cc, o;         // conic yy, opacity          (geomState.conic_opacity)
-  float col, invd;     // colour (1 channel), 1/depth
+  float o, col;        // opacity (conic_opacity.w), colour (1 channel)
   float m0, m1, m2, m3;// all_map channels
 };
 static_assert(sizeof(Rec) == 48, "record must stay 48 bytes");
@@ -189,8 +193,7 @@ struct SortBufs {
 };
 
 struct GeomState {
-  float2* xy;
-  float4* conic_o;
+  Rec* grec;         // per Gaussian: conic, 1/depth, mean2D, opacity, colour, all_map (valid where tiles > 0)
   float* depth;
   uint32_t* tiles;
   uint2* rect;       // packed tile rect: x = min.x | min.y<<16, y = max.x | max.y<<16
@@ -202,8 +205,7 @@ struct GeomState {
     Carver c(base);
     GeomState g;
     int64_t nblk = (P + 255) / 256;
-    g.xy = c.take<float2>(P);
-    g.conic_o = c.take<float4>(P);
+    g.grec = c.take<Rec>(P + 1);
     g.depth = c.take<float>(P);
     g.tiles = c.take<uint32_t>(P);
     g.rect = c.take<uint2>(P);
@@ -248,18 +250,19 @@ struct ImgState {
 };
 
 struct BinKeep {
-  Rec* rec;
-  uint32_t* point_list;
+  uint32_t* point_list;   // Gaussian index per sorted tile-instance (the reference's point_list)
   // Candidate lists of the 8x4 pixel blocks: block b (0..7) of a tile whose range is [x, y) owns
   // cand[8 * x + b * (y - x) ...]: the tile-relative list positions, ascending, of the instances that passed the
-  // forward's block_candidate test for that block (written by blend_fwd, consumed back to front by blend_bwd_ring).
+  // forward's block_candidate test for that block, and cand_id[...] their Gaussian indices (written by blend_fwd,
+  // consumed back to front by blend_bwd_ring).
   uint32_t* cand;
+  uint32_t* cand_id;
   static BinKeep carve(void* base, int64_t R, size_t* bytes) {
     Carver c(base);
     BinKeep b;
-    b.rec = c.take<Rec>(R + 1);
     b.point_list = c.take<uint32_t>(R + 1);
     b.cand = c.take<uint32_t>(8 * size_t(R + 1));
+    b.cand_id = c.take<uint32_t>(8 * size_t(R + 1));
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }
@@ -302,7 +305,9 @@ inline uint32_t tile_key_bits(uint32_t n) {
 // and buffers are sized for (sync-free binning, cg_raster_fwd_capacity).
 template <typename K>
 int radix_sort_pairs(const SortBufs<K>& b, int64_t n, int end_bit, int* out_buf, bool debug, cudaStream_t stream,
-                     const uint32_t* d_n = nullptr, bool hist_ready = false);
+                     const uint32_t* d_n = nullptr, bool hist_ready = false, uint32_t* final_vals = nullptr);
+// (final_vals != NULL: the last pass writes the sorted VALUES there instead of into its ping-pong buffer; the sorted
+//  keys still land in b.keys[*out_buf])
 // A producer that writes b.keys[0] can fill the digit histograms itself: radix_sort_begin (clears b.hist and the
 // look-back state) -> producer adds, for every key and pass p, one count to b.hist[p * 256 + digit_p(key)]
 // (digit geometry from radix_sort_geometry) -> radix_sort_pairs(..., hist_ready = true) skips its histogram pass.

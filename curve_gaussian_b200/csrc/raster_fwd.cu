@@ -25,7 +25,8 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
                const float* __restrict__ cov3D_precomp, float scale_modifier,
                const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
                int W, int H, float tanx, float tany, float fx, float fy, int grid_x, int grid_y,
-               int antialiasing, int32_t* __restrict__ radii, GeomState g) {
+               int antialiasing, const float* __restrict__ colors, const float* __restrict__ all_map,
+               int32_t* __restrict__ radii, GeomState g) {
   pdl_wait();
   __shared__ __align__(16) float s_mean[768];
   __shared__ __align__(16) float s_scale[768];
@@ -93,8 +94,11 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
           touched = area;
           radius_out = rad;
           g.depth[idx] = p_view.z;
-          g.xy[idx] = make_float2(pix_x, pix_y);
-          g.conic_o[idx] = make_float4(conic.x, conic.y, conic.z, __ldg(opacities + idx) * h_scaling);
+          // the record the blend kernels gather by Gaussian index: three 16-byte stores
+          float4* rec = reinterpret_cast<float4*>(g.grec + idx);
+          rec[0] = make_float4(conic.x, conic.y, conic.z, 1.f / p_view.z);
+          rec[1] = make_float4(pix_x, pix_y, __ldg(opacities + idx) * h_scaling, colors ? __ldg(colors + idx) : 0.f);
+          rec[2] = all_map ? __ldg(reinterpret_cast<const float4*>(all_map) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
           g.rect[idx] = make_uint2(uint32_t(mnx) | (uint32_t(mny) << 16), uint32_t(mxx) | (uint32_t(mxy) << 16));
         }
       }
@@ -264,52 +268,38 @@ rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_
   keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
 }
 
-// One sorted instance: tile range boundaries, point list entry, and its 48-byte record into the CTA's staging area.
-__device__ __forceinline__ void
-gather_one(int64_t i, int64_t R, const uint32_t* __restrict__ sorted_tiles, const uint32_t* __restrict__ sorted_vals,
-           const GeomState& g, const float* __restrict__ colors, const float* __restrict__ all_map,
-           uint2* __restrict__ ranges, uint32_t* __restrict__ point_list, float4* s_out) {
-  if (i >= R) return;
-  {
-    // per-tile [start, end) into the sorted list (rasterizer_impl.cu:116-138); ranges is zero-filled
-    const uint32_t cur = sorted_tiles[i];
-    if (i == 0) ranges[cur].x = 0;
-    else {
-      const uint32_t prev = sorted_tiles[i - 1];
-      if (cur != prev) { ranges[prev].y = uint32_t(i); ranges[cur].x = uint32_t(i); }
-    }
-    if (i == R - 1) ranges[cur].y = uint32_t(R);
-  }
-  const uint32_t id = sorted_vals[i];
-  point_list[i] = id;
-  const float2 xy = g.xy[id];
-  const float4 co = g.conic_o[id];
-  float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (all_map) mp = __ldg(reinterpret_cast<const float4*>(all_map) + id);
-  // the CTA's 256 records are one contiguous 12 KB span: stage them in shared memory (16-byte words at stride 3:
-  // conflict-free) and write the span with consecutive 128-bit stores instead of 48-byte-strided ones
-  s_out[threadIdx.x * 3 + 0] = make_float4(xy.x, xy.y, co.x, co.y);
-  s_out[threadIdx.x * 3 + 1] = make_float4(co.z, co.w, __ldg(colors + id), 1.f / g.depth[id]);
-  s_out[threadIdx.x * 3 + 2] = mp;
-}
-
-// Sorted instance i -> tile range boundaries + contiguous 48-byte record + point list entry.
+// Per-tile [start, end) into the sorted list (rasterizer_impl.cu:116-138); ranges is zero-filled.
+// Four keys per thread (one 128-bit load) and a grid-stride loop over a grid of a few CTAs per SM: with one key per
+// thread the kernel is bound by the launch rate of its 34 000 tiny CTAs (38 us at C4), not by its 35 MB.
 __global__ void __launch_bounds__(256)
-gather_records(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __restrict__ sorted_tiles,
-               const uint32_t* __restrict__ sorted_vals, GeomState g, const float* __restrict__ colors,
-               const float* __restrict__ all_map, uint2* __restrict__ ranges, Rec* __restrict__ rec,
-               uint32_t* __restrict__ point_list) {
+tile_ranges(int64_t R, const uint32_t* __restrict__ d_n, const uint32_t* __restrict__ sorted_tiles,
+            uint2* __restrict__ ranges) {
   pdl_wait();
-  __shared__ float4 s_out[256 * 3];
   if (d_n) R = min(R, int64_t(*d_n));   // capacity mode: the count lives on the device
-  const int64_t blk0 = int64_t(blockIdx.x) * 256;
-  if (blk0 >= R) return;
-  const int64_t i = blk0 + threadIdx.x;
-  gather_one(i, R, sorted_tiles, sorted_vals, g, colors, all_map, ranges, point_list, s_out);
-  __syncthreads();
-  const int nvec = int(min(int64_t(256), R - blk0)) * 3;
-  float4* dst = reinterpret_cast<float4*>(rec + blk0);
-  for (int k = threadIdx.x; k < nvec; k += 256) dst[k] = s_out[k];
+  const int64_t nquad = (R + 3) >> 2;
+  for (int64_t q = int64_t(blockIdx.x) * 256 + threadIdx.x; q < nquad; q += int64_t(gridDim.x) * 256) {
+    const int64_t i0 = q << 2;
+    uint32_t k[4];
+    if (i0 + 3 < R) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sorted_tiles + i0);   // (the key buffers are 128-byte aligned)
+      k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = (i0 + j < R) ? sorted_tiles[i0 + j] : 0u;
+    }
+    uint32_t prev = i0 > 0 ? sorted_tiles[i0 - 1] : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = i0 + j;
+      if (i < R) {
+        const uint32_t cur = k[j];
+        if (i == 0) ranges[cur].x = 0;
+        else if (cur != prev) { ranges[prev].y = uint32_t(i); ranges[cur].x = uint32_t(i); }
+        if (i == R - 1) ranges[cur].y = uint32_t(R);
+        prev = cur;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -382,24 +372,32 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* _
   }
 }
 
-// BLEND_SUBS CTAs per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block. The tile's
-// sorted records are one contiguous span; thread 0 streams it into a 2-deep shared ring with
-// cp.async.bulk while all threads blend the previous batch. Each warp first tests 32 records
-// at a time (one per lane, block_candidate in common.cuh) against its pixel block and only
+// One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block.
+// Staging, three batches deep: thread 0 streams the tile's sorted Gaussian list (the ids: one contiguous span of
+// point_list) into a shared ring with cp.async.bulk (TMA 1-D bulk copy + mbarrier) two batches ahead; one batch
+// ahead every thread gathers ITS record of the batch from the per-Gaussian table (GeomState::grec, L2-resident)
+// with 16-byte cp.async copies straight into shared memory; the current batch is blended. Each warp first
+// tests 32 records at a time (one per lane, block_candidate in common.cuh) against its pixel block and only
 // walks the instances that can reach it, in list order (forward.cu:331-396 semantics).
 #ifndef CG_FWD_CTAS
 #define CG_FWD_CTAS 6
 #endif
+__device__ __forceinline__ void fwd_cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
 template <bool GEO>
 __global__ void __launch_bounds__(BLEND_THREADS, CG_FWD_CTAS * (256 / BLEND_THREADS))
 blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int grid_x,
-          const Rec* __restrict__ rec, int W, int H, const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
+          const Rec* __restrict__ grec, const uint32_t* __restrict__ point_list, int W, int H,
+          const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-          uint32_t* __restrict__ tile_maxc, uint32_t* __restrict__ cand_lists, uint32_t* __restrict__ blk_cnt,
-          uint32_t* __restrict__ cls_count, uint32_t* __restrict__ cls_list, uint32_t nblocks) {
+          uint32_t* __restrict__ tile_maxc, uint32_t* __restrict__ cand_lists, uint32_t* __restrict__ cand_ids,
+          uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ cls_count, uint32_t* __restrict__ cls_list,
+          uint32_t nblocks) {
   pdl_wait();
   __shared__ __align__(128) Rec s_rec[2][BATCH];
-  __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ __align__(128) uint32_t s_ids[3][BATCH + 8];   // (+ the alignment slack of the bulk copy's source)
+  __shared__ __align__(8) uint64_t s_full[3];
   __shared__ uint32_t s_maxc;
 
   const uint32_t cta = tile_order[blockIdx.x];
@@ -423,42 +421,80 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   if (tid == 0) {
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
+    mbar_init(&s_full[2], 1);
     mbar_fence_init();
     s_maxc = 0;
   }
   __syncthreads();
-  if (tid == 0 && rounds > 0) {
-    const uint32_t nb = uint32_t(min(BATCH, total));
-    mbar_expect_tx(&s_full[0], nb * uint32_t(sizeof(Rec)));
-    bulk_g2s(&s_rec[0][0], rec + range.x, nb * uint32_t(sizeof(Rec)), &s_full[0]);
+  // ids of batch k: TMA bulk copy of point_list[range.x + k * BATCH, +n) into s_ids[k % 3]. A bulk copy moves
+  // 16-byte granules from a 16-byte aligned source, so it starts at the aligned address below the span (ids_off
+  // entries early, the same for every batch) and is rounded up at the end; point_list is padded, the surplus
+  // entries are never used.
+  const uint32_t ids_off = range.x & 3u;
+  auto issue_ids = [&](int k) {
+    const uint32_t nb = uint32_t(min(BATCH, total - k * BATCH));
+    const uint32_t bytes = (((ids_off + nb) * 4u) + 15u) & ~15u;
+    const uint32_t* src = point_list + (size_t(range.x) - ids_off) + size_t(k) * BATCH;
+    mbar_expect_tx(&s_full[k % 3], bytes);
+    bulk_g2s(&s_ids[k % 3][0], src, bytes, &s_full[k % 3]);
+  };
+  // (ring slot 0 is first used by batch 3: batch 0 takes its ids with plain loads, see below)
+  auto ids_parity = [](int k) { return uint32_t(k / 3 + (k % 3 == 0 ? 1 : 0)) & 1u; };
+  // records of batch k: every thread gathers the record of its slot
+  auto issue_records = [&](int k) {
+    mbar_wait(&s_full[k % 3], ids_parity(k));
+    const int nb = min(BATCH, total - k * BATCH);
+    if (int(tid) < nb) {
+      const Rec* r = grec + s_ids[k % 3][ids_off + tid];
+      Rec* d = &s_rec[k & 1][tid];
+      fwd_cp_async16(&d->ca, &r->ca);
+      fwd_cp_async16(&d->x, &r->x);
+      if (GEO) fwd_cp_async16(&d->m0, &r->m0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (rounds > 0) {
+    if (tid == 0) { if (rounds > 1) issue_ids(1); if (rounds > 2) issue_ids(2); }
+    // batch 0 takes its ids with plain loads: one L2 round trip less before the first record can be gathered, which
+    // is most of the life of the many short tiles
+    const int nb = min(BATCH, total);
+    if (int(tid) < nb) {
+      const uint32_t id = point_list[size_t(range.x) + tid];
+      s_ids[0][ids_off + tid] = id;
+      const Rec* r = grec + id;
+      Rec* d = &s_rec[0][tid];
+      fwd_cp_async16(&d->ca, &r->ca);
+      fwd_cp_async16(&d->x, &r->x);
+      if (GEO) fwd_cp_async16(&d->m0, &r->m0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   bool done = !inside;
   float T = 1.0f, C = 0.f, invd_acc = 0.f;
   float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3v = 0.f;
   uint32_t last_contributor = 0;
-  // candidate list of this warp's 8x4 block (BinKeep::cand): tile-relative positions of the instances that pass the
-  // block test, in list order; cand_eff = how many of them lie at or below the block's last contributor
-  // (32-bit offsets into cand_lists: the kernel runs at 40 registers)
+  // candidate list of this warp's 8x4 block (BinKeep::cand / cand_id): tile-relative positions and Gaussian ids of
+  // the instances that pass the block test, in list order; cand_eff = how many of them lie at or below the block's
+  // last contributor
+  // (32-bit offsets into the lists: the kernel runs at 40 registers)
   const uint32_t cand_start = 8u * range.x + (sub * BLEND_WARPS + warp) * uint32_t(total);
   uint32_t cand_off = cand_start, cand_eff = cand_start;
 
   int todo = total;
   for (int b = 0; b < rounds; ++b, todo -= BATCH) {
-    const int num_done = __syncthreads_count(done);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");     // this thread's record of batch b has landed
+    const int num_done = __syncthreads_count(done);          // ... and everybody's is visible
     if (num_done == BLEND_THREADS) {
-      // batch b is (or was) in flight: drain it before the CTA retires
-      if (tid == 0) mbar_wait(&s_full[b & 1], (b >> 1) & 1);
+      // id spans still in flight (batch b+1; in the first iteration also batch 2): drain them before the CTA retires
+      if (tid == 0 && b + 1 < rounds) mbar_wait(&s_full[(b + 1) % 3], ids_parity(b + 1));
+      if (tid == 0 && b == 0 && rounds > 2) mbar_wait(&s_full[2], ids_parity(2));
       break;
     }
-    if (tid == 0 && b + 1 < rounds) {
-      const uint32_t nb = uint32_t(min(BATCH, todo - BATCH));
-      const size_t off = size_t(range.x) + size_t(b + 1) * BATCH;
-      mbar_expect_tx(&s_full[(b + 1) & 1], nb * uint32_t(sizeof(Rec)));
-      bulk_g2s(&s_rec[(b + 1) & 1][0], rec + off, nb * uint32_t(sizeof(Rec)), &s_full[(b + 1) & 1]);
-    }
-    mbar_wait(&s_full[b & 1], (b >> 1) & 1);
+    if (b + 1 < rounds) issue_records(b + 1);
+    if (tid == 0 && b > 0 && b + 2 < rounds) issue_ids(b + 2);   // (batches 1 and 2 were requested in the prologue)
     const Rec* batch = s_rec[b & 1];
+    const uint32_t* ids = s_ids[b % 3] + ids_off;
     const int n = min(BATCH, todo);
     const uint32_t pos0 = uint32_t(b) * BATCH;
     for (int r = 0; r < n; r += 32) {
@@ -466,34 +502,35 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
       const int idx = r + int(lane);
       bool cand = false;
       if (idx < n) {
-        const float4 ca = *reinterpret_cast<const float4*>(&batch[idx].x);
-        const float2 cb = *reinterpret_cast<const float2*>(&batch[idx].cc);
-        cand = block_candidate(ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, bx0, bx1, by0, by1);
+        const float4 q0 = *reinterpret_cast<const float4*>(&batch[idx].ca);   // ca cb cc invd
+        const float4 q1 = *reinterpret_cast<const float4*>(&batch[idx].x);    // x y o col
+        cand = block_candidate(q1.x, q1.y, q0.x, q0.y, q0.z, q1.z, bx0, bx1, by0, by1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, cand);
       if (cand) {
         uint32_t below;   // candidates in lower lanes (shl clamps: lane 0 shifts everything out)
         asm("shl.b32 %0, %1, %2;" : "=r"(below) : "r"(mask), "r"(32u - lane));
-        cand_lists[cand_off + __popc(below)] = pos0 + uint32_t(idx);
+        const uint32_t at = cand_off + __popc(below);
+        cand_lists[at] = pos0 + uint32_t(idx);
+        cand_ids[at] = ids[idx];
       }
       while (mask) {
         const int j = r + __ffs(int(mask)) - 1;
         mask &= mask - 1;
         if (!done) {
-          const float4 a = *reinterpret_cast<const float4*>(&batch[j].x);    // x y ca cb
-          const float2 c2 = *reinterpret_cast<const float2*>(&batch[j].cc);  // cc o
-          const float dx = __fsub_rn(a.x, pxf), dy = __fsub_rn(a.y, pyf);
-          const float power = gauss_power(a.z, a.w, c2.x, dx, dy);
+          const float4 q0 = *reinterpret_cast<const float4*>(&batch[j].ca);   // ca cb cc invd
+          const float4 q1 = *reinterpret_cast<const float4*>(&batch[j].x);    // x y o col
+          const float dx = __fsub_rn(q1.x, pxf), dy = __fsub_rn(q1.y, pyf);
+          const float power = gauss_power(q0.x, q0.y, q0.z, dx, dy);
           if (!(power > 0.0f)) {
-            const float alpha = fminf(0.99f, __fmul_rn(c2.y, expf(power)));
+            const float alpha = fminf(0.99f, __fmul_rn(q1.z, expf(power)));
             if (!(alpha < 1.0f / 255.0f)) {
               const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
               if (test_T < 0.0001f) {
                 done = true;
               } else {
-                const float2 ci = *reinterpret_cast<const float2*>(&batch[j].col);  // col invd
-                C = __fmaf_rn(__fmul_rn(ci.x, alpha), T, C);
-                invd_acc = __fmaf_rn(__fmul_rn(ci.y, alpha), T, invd_acc);
+                C = __fmaf_rn(__fmul_rn(q1.w, alpha), T, C);
+                invd_acc = __fmaf_rn(__fmul_rn(q0.w, alpha), T, invd_acc);
                 if (GEO) {
                   const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
                   M0 = __fmaf_rn(__fmul_rn(mp.x, alpha), T, M0);
@@ -518,6 +555,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // (a gather issued for a batch the CTA did not reach)
 
   if (inside) {
     final_T[pix_id] = T;
@@ -563,8 +601,8 @@ mark_visible_kernel(int64_t P, const float* __restrict__ means3D, const float* _
 // ---------------------------------------------------------------------------
 // host side
 int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
-                    const float* scales, const float* rotations, const float* cov3D_precomp,
-                    int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st) {
+                    const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
+                    const float* all_map, int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st) {
   GeomState g = GeomState::carve(geom, P, nullptr);
   const int W = s->image_width, H = s->image_height;
   const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
@@ -573,7 +611,8 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   { StageTimer t_(ST_PREPROCESS_FWD, st, 1);
   launch_k(preprocess_fwd, dim3(unsigned(nblk)), dim3(256), 0, st, P, means3D, opacities, scales, rotations, cov3D_precomp,
                                                  s->scale_modifier, s->viewmatrix, s->projmatrix, W, H, s->tanfovx,
-                                                 s->tanfovy, fx, fy, gx, gy, s->antialiasing, radii, g); }
+                                                 s->tanfovy, fx, fy, gx, gy, s->antialiasing, colors,
+                                                 s->render_geo ? all_map : nullptr, radii, g); }
   CG_LAUNCH_CHECK(s->debug, st);
   { StageTimer t_(ST_SCAN, st, 1);
   launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g); }
@@ -619,8 +658,7 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
 // nr_out == NULL: R is the exact instance count (known on the host). nr_out != NULL (capacity mode): R is the
 // capacity of bin_keep / bin_scratch, the true count is read on the device (g.total) by every R-sized kernel and
 // {count, overflow} is written to nr_out.
-int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const float* colors, const float* all_map,
-                     void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
+int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* geom, void* img, void* bin_keep, void* bin_scratch, float* out_color, float* out_invd,
                      float* out_map, uint32_t* nr_out, cudaStream_t st) {
   const uint32_t* d_n = nr_out ? GeomState::carve(geom, P, nullptr).total : nullptr;
   GeomState g = GeomState::carve(geom, P, nullptr);
@@ -651,12 +689,12 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
              uint32_t(R), nr_out, fused_hist ? bs.is.hist : nullptr, bpp); }
     CG_LAUNCH_CHECK(s->debug, st);
     { StageTimer t_(ST_SORT, st, 0);
-    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_n, fused_hist); }
+    // (its last pass leaves the sorted Gaussian indices directly in the point list that the backward keeps)
+    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_n, fused_hist, bk.point_list); }
     if (rc != CG_OK) return rc;
-    const unsigned rb = unsigned((R + 255) / 256);
-    { StageTimer t_(ST_GATHER, st, 1);
-    launch_k(gather_records, dim3(rb), dim3(256), 0, st, R, d_n, bs.is.keys[cur], bs.is.vals[cur], g, colors,
-                                       s->render_geo ? all_map : nullptr, im.ranges, bk.rec, bk.point_list); }
+    const unsigned rb = unsigned(min(int64_t(148 * 16), (R + 1023) / 1024));
+    { StageTimer t_(ST_TILE_RANGES, st, 1);
+    launch_k(tile_ranges, dim3(rb), dim3(256), 0, st, R, d_n, bs.is.keys[cur], im.ranges); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   const dim3 grid{unsigned(tiles) * BLEND_SUBS, 1u, 1u}, block{unsigned(BLEND_THREADS), 1u, 1u};
@@ -664,11 +702,13 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, const fl
   launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
   CG_LAUNCH_CHECK(s->debug, st);
   if (s->render_geo)
-    launch_k(blend_fwd<true>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
-                                            out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, im.blk_cnt, im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
+    launch_k(blend_fwd<true>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, g.grec, bk.point_list, W, H, s->bg,
+             out_color, out_invd, out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, bk.cand_id, im.blk_cnt,
+             im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
   else
-    launch_k(blend_fwd<false>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, bk.rec, W, H, s->bg, out_color, out_invd,
-                                             out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, im.blk_cnt, im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
+    launch_k(blend_fwd<false>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, g.grec, bk.point_list, W, H, s->bg,
+             out_color, out_invd, out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, bk.cand_id, im.blk_cnt,
+             im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
   CG_LAUNCH_CHECK(s->debug, st);
   return CG_OK;
 }

@@ -282,7 +282,7 @@ int radix_sort_begin(const SortBufs<K>& b, int64_t R, int end_bit, cudaStream_t 
 
 template <typename K>
 int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf, bool debug, cudaStream_t stream,
-                     const uint32_t* d_n, bool hist_ready) {
+                     const uint32_t* d_n, bool hist_ready, uint32_t* final_vals) {
   *out_buf = 0;
   if (R <= 0) return CG_OK;
   if (R >= (int64_t(1) << FLAG_SHIFT)) {
@@ -318,7 +318,7 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
 
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
-    launch_k(sort_onesweep_pass<K>, dim3(unsigned(ntiles)), dim3(SORT_THREADS), sizeof(SortSmem<K>), stream, b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1], R, d_n, bpp * p, dmask,
+    launch_k(sort_onesweep_pass<K>, dim3(unsigned(ntiles)), dim3(SORT_THREADS), sizeof(SortSmem<K>), stream, b.keys[cur], b.vals[cur], b.keys[cur ^ 1], (final_vals && p == passes - 1) ? final_vals : b.vals[cur ^ 1], R, d_n, bpp * p, dmask,
         b.hist + p * 256, b.ticket + p, b.status + size_t(p) * ntiles * 256);
     CG_LAUNCH_CHECK(debug, stream);
     cur ^= 1;
@@ -327,8 +327,8 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
   return CG_OK;
 }
 
-template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*, bool);
-template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*, bool);
+template int radix_sort_pairs<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*, bool, uint32_t*);
+template int radix_sort_pairs<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, int*, bool, cudaStream_t, const uint32_t*, bool, uint32_t*);
 template int radix_sort_begin<uint32_t>(const SortBufs<uint32_t>&, int64_t, int, cudaStream_t);
 template int radix_sort_begin<uint64_t>(const SortBufs<uint64_t>&, int64_t, int, cudaStream_t);
 

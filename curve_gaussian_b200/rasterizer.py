@@ -68,6 +68,19 @@ def _bytes(n: int, device) -> torch.Tensor:
     return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
 
 
+def _alloc_instances(R: int) -> int:
+    """Instance count to SIZE the R-dependent buffers for: R rounded up to the next of {1, 1.25, 1.5, 1.75} x 2^k.
+    R changes from view to view; with exact sizes every view that needs more than any before it sends the caching
+    allocator to cudaMalloc (a device synchronisation, milliseconds), for as long as new maxima keep arriving. With a
+    handful of distinct sizes the blocks of the first few views serve all later ones."""
+    R = max(int(R), 1)
+    k = max(R.bit_length() - 1, 2)
+    for q in (4, 5, 6, 7, 8):
+        if R <= (q << (k - 2)):
+            return q << (k - 2)
+    return R
+
+
 def _capturing() -> bool:
     return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
@@ -284,12 +297,14 @@ def rasterize_forward_raw(rs, means3D, colors_precomp, opacities, scales, rotati
     R = C.c_int64(0)
     with _lib.on_device(dev):
         _lib.check(lib.cg_raster_fwd_geom(C.byref(s), P, _lib.ptr(means3D), _lib.ptr(opacities), _lib.ptr(scales),
-                                          _lib.ptr(rotations), _lib.ptr(cov3D), _lib.ptr(radii), geom.data_ptr(),
-                                          geom.numel(), C.byref(R), stream), "cg_raster_fwd_geom")
+                                          _lib.ptr(rotations), _lib.ptr(cov3D), _lib.ptr(colors), _lib.ptr(amap),
+                                          _lib.ptr(radii), geom.data_ptr(), geom.numel(), C.byref(R), stream),
+                   "cg_raster_fwd_geom")
         R = int(R.value)
-        bin_keep = _bytes(lib.cg_raster_bin_keep_bytes(R), dev)
-        bin_scratch = _bytes(lib.cg_raster_bin_scratch_bytes(P, R), dev)
-        _lib.check(lib.cg_raster_fwd_blend(C.byref(s), P, R, _lib.ptr(colors), _lib.ptr(amap), geom.data_ptr(),
+        Ra = _alloc_instances(R)     # (the layout inside the buffers follows R; only their size is rounded up)
+        bin_keep = _bytes(lib.cg_raster_bin_keep_bytes(Ra), dev)
+        bin_scratch = _bytes(lib.cg_raster_bin_scratch_bytes(P, Ra), dev)
+        _lib.check(lib.cg_raster_fwd_blend(C.byref(s), P, R, geom.data_ptr(),
                                            img.data_ptr(), bin_keep.data_ptr(), bin_scratch.data_ptr(),
                                            color.data_ptr(), invdepth.data_ptr(), out_all_map.data_ptr(), stream),
                    "cg_raster_fwd_blend")

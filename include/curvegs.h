@@ -94,6 +94,8 @@ size_t cg_raster_bin_scratch_bytes(int64_t P, int64_t R);
  * through *num_rendered (host int). Like rasterizer_impl.cu:287 this call waits for that
  * 4-byte read, but on an event recorded right behind the copy, so the depth sort keeps
  * the GPU busy while the host wakes up and allocates the R-sized buffers.
+ * It also writes the per-Gaussian record the blend kernels later gather by Gaussian index (conic, 1/depth,
+ * mean2D, opacity, colour, all_map), which is why the colour and all_map arrays arrive here.
  * Exactly one of (scales+rotations) / cov3D_precomp must be non-NULL. */
 int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P,
                        const float* means3D,      /* (P,3) */
@@ -101,6 +103,8 @@ int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P,
                        const float* scales,       /* (P,3) or NULL */
                        const float* rotations,    /* (P,4) raw quaternion, or NULL */
                        const float* cov3D_precomp,/* (P,6) or NULL */
+                       const float* colors,       /* (P) single colour channel (colors_precomp) */
+                       const float* all_map,      /* (P,4), 16-byte aligned; NULL unless render_geo */
                        int32_t* radii,            /* out (P) */
                        void* geom, size_t geom_bytes,
                        int64_t* num_rendered,     /* out, host */
@@ -108,10 +112,9 @@ int cg_raster_fwd_geom(const cg_raster_settings* s, int64_t P,
 
 /* Forward, stage 2: depth-sort the Gaussians -> duplicate per tile -> stable radix
  * sort by tile (same permutation as the reference's 64-bit tile|depth sort) -> tile
- * ranges -> record gather -> per-tile front-to-back blend. colors is (P,1); all_map is (P,4)
- * or NULL when !render_geo. Outputs are (1,H,W), (1,H,W), (4,H,W). */
+ * ranges -> per-tile front-to-back blend (records gathered by Gaussian index from the geom state).
+ * Outputs are (1,H,W), (1,H,W), (4,H,W). */
 int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R,
-                        const float* colors, const float* all_map,
                         void* geom, void* img,
                         void* bin_keep, void* bin_scratch,
                         float* out_color, float* out_invdepth, float* out_all_map,

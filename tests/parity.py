@@ -65,8 +65,9 @@ def frac_beyond(a, b, thresh=1e-4, floor=1e-5):
     return float((((a - b).abs() / (b.abs() + floor * mx)) > thresh).double().mean())
 
 
-def check(file, case, name, ours, ref, ref_again=(), tol=1e-5):
-    """Assert ours == ref as described in the module docstring; record every figure."""
+def check(file, case, name, ours, ref, ref_again=(), tol=1e-5, assert_share=True):
+    """Assert ours == ref as described in the module docstring; record every figure. assert_share=False: the two sides
+    did not get bit-identical inputs (a stage upstream differs by an ulp), so only max-rel is asserted."""
     err, err_el = max_rel(ours, ref), rel_err(ours, ref)
     noise = max([max_rel(r, ref) for r in ref_again], default=0.0)
     noise_el = max([rel_err(r, ref) for r in ref_again], default=0.0)
@@ -76,7 +77,7 @@ def check(file, case, name, ours, ref, ref_again=(), tol=1e-5):
            bit_identical=bool(torch.equal(torch.as_tensor(ours).cpu(), torch.as_tensor(ref).cpu())))
     assert err <= max(tol, NOISE_FACTOR * noise), (
         f"{case}/{name}: max-rel err {err:.3e} > max({tol:g}, {NOISE_FACTOR:g} x reference self-noise {noise:.3e})")
-    assert fb <= max(1e-3, 5 * fb_noise), (
+    assert (not assert_share) or fb <= max(1e-3, 5 * fb_noise), (
         f"{case}/{name}: {fb:.2e} of the elements are off by more than 1e-4 of their own magnitude "
         f"(between two reference runs: {fb_noise:.2e})")
     return err, noise

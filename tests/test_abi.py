@@ -52,7 +52,7 @@ def test_bad_arguments_return_error_codes_not_crashes():
     import ctypes as C
     s = _lib.RasterSettings()
     R = C.c_int64(0)
-    rc = lib.cg_raster_fwd_geom(C.byref(s), 10, None, None, None, None, None, None, None, 0, C.byref(R), None)
+    rc = lib.cg_raster_fwd_geom(C.byref(s), 10, None, None, None, None, None, None, None, None, None, 0, C.byref(R), None)
     assert rc == -1
     assert b"image size" in lib.cg_last_error()
 
