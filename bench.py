@@ -218,7 +218,7 @@ def run_ours(a):
     # one flat fp32 gradient buffer [curve_points | width | opacity | mask]; .grad tensors are views into it,
     # so backward accumulates in place and the all-reduce needs no pack copy
     from curve_gaussian_b200.parallel import FlatGrad
-    fg = FlatGrad([model._curve_points, model._width, model._opacity, model._mask])
+    fg = FlatGrad([model._curve_points, model._width, model._opacity, model._mask], direct=True)
     flat = fg.flat
     flat_host = torch.empty(flat.shape, dtype=flat.dtype).pin_memory()
 
@@ -423,9 +423,16 @@ def run_ours(a):
         par = parity_vs_reference(model, cams[0], bg, dev)
         if par:
             out["parity"] = par
-            out["grad_max_rel_err"] = par.get("grad_max_rel_err")
         if world == 1 and not a.no_reference_step:
-            out["reference_gpu_step"] = reference_gpu_step(a, ms / K)
+            rg = reference_gpu_step(a, ms / K / V, dev)
+            out["reference_gpu_step"] = rg
+            if "grad_parity" in rg:
+                # BASELINE.json metric, third component: dL/dcontrol-points against the reference's real step
+                out["grad_max_rel_err"] = rg["grad_parity"]["dL_dcurve_points"]["max_rel_err"]
+        if "grad_max_rel_err" not in out and par:
+            out["grad_max_rel_err"] = par.get("grad_max_rel_err")
+        out["hbm_gbs_vs_peak"] = {"achieved_GBps": out["hbm_algorithmic"]["achieved_GBps"], "peak_GBps": peak,
+                                  "frac": out["hbm_algorithmic"]["frac_of_peak_per_gpu"]}
         if world == 1 and not a.no_small_scene:
             out["small_scene_step"] = small_scene_step(dev, pipe)
         print(json.dumps(out))
@@ -447,7 +454,7 @@ def small_scene_step(dev, pipe, B=417, n=12, W=800, H=800, steps=60, nviews=8):
         from curve_gaussian_b200.renderer import render
         cp, width, opl, isb = synth.random_curves(B, seed=0)
         model = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb)
-        fg = FlatGrad([model._curve_points, model._width, model._opacity, model._mask])
+        fg = FlatGrad([model._curve_points, model._width, model._opacity, model._mask], direct=True)
         bg = torch.zeros(3, device=dev)
         cams = [c.to(dev) for c in synth.random_cameras(nviews, W, H, seed=0)]
         gts = [torch.rand(1, H, W, device=dev) for _ in cams]
@@ -591,23 +598,48 @@ def parity_vs_reference(model, cam, bg, dev):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
-def reference_gpu_step(a, our_ms):
+def reference_gpu_step(a, our_ms, dev):
     """Baselines B1 + B2 of BASELINE.md together: the reference's OWN Python step (its torch sampling, render() with the
-    reference CUDA rasterizer recompiled for sm_100, its edge loss + fused-ssim, autograd backward) timed on this GPU
-    by oracle/ref_step.py in a subprocess, on the same curve set and image size as the benchmarked workload."""
+    reference CUDA rasterizer recompiled for sm_100, its edge loss + fused-ssim, autograd backward) run on this GPU
+    by oracle/ref_step.py in a subprocess, on the same curve set and image size as the benchmarked workload. Gives
+    (a) its time per step and (b) - the metric's third component - dL/d{control points, width, opacity} of the repo's
+    step against the reference's on the same inputs, next to the reference's own run-to-run difference."""
     try:
         import tempfile
+        import numpy as np
         spec = {"B": a.curves, "n": a.samples, "W": a.width, "H": a.height, "seed": 0, "cam_seed": 0}
         with tempfile.TemporaryDirectory() as td:
+            out = os.path.join(td, "o.npz")
             r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_step.py"), "--spec", json.dumps(spec),
-                                "--out", os.path.join(td, "o.npz"), "--repeats", "1", "--time-steps", "10"],
+                                "--out", out, "--repeats", "3", "--time-steps", "10"],
                                capture_output=True, text=True, timeout=600)
-        if r.returncode != 0:
-            return {"error": (r.stderr or r.stdout)[-300:]}
-        ms = json.loads(r.stdout.strip().splitlines()[-1])["ms_per_step"]
-        return {"what": "reference train.py step (prepare_scaling_rot -> render -> edge loss + fused_ssim -> backward), "
-                        "unmodified reference Python + reference CUDA recompiled for sm_100, same GPU, ms per step",
-                "reference_ms_per_step": round(ms, 3), "ours_ms_per_step": round(our_ms, 4), "speedup": round(ms / our_ms, 2)}
+            if r.returncode != 0:
+                return {"error": (r.stderr or r.stdout)[-300:]}
+            with np.load(out) as z:
+                ref = {k: z[k] for k in z.files}
+        ms = float(ref["ms_per_step"])
+        res = {"what": "reference train.py step (prepare_scaling_rot -> render -> edge loss + fused_ssim -> backward), "
+                       "unmodified reference Python + reference CUDA recompiled for sm_100, same GPU, ms per step",
+               "reference_ms_per_step": round(ms, 3), "ours_ms_per_step": round(our_ms, 4), "speedup": round(ms / our_ms, 2)}
+        # the same step through the repo, same curve set / camera / edge map: gradients of the curve parameters
+        from tests import parity as PT
+        from tests import test_gpu_reference_step as TS
+        gt = torch.from_numpy(ref["gt"]).to(dev)
+        m, cam = TS.build_repo_model(spec, dev)
+        m.prepare_scaling_rot()
+        pkg, loss = TS.repo_render_loss(m, cam, spec, gt)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {}
+        for name, p_ in (("curve_points", m._curve_points), ("width", m._width), ("opacity", m._opacity)):
+            g = p_.grad.detach().cpu().reshape(-1)
+            b = torch.from_numpy(ref["g_" + name]).reshape(-1)
+            grads["dL_d" + name] = {
+                "max_rel_err": float(f"{PT.max_rel(g, b):.3e}"),
+                "ref_self_noise": float(f"{max(PT.max_rel(torch.from_numpy(ref[f'g_{name}_run{k}']).reshape(-1), b) for k in (1, 2)):.3e}")}
+        res["grad_parity"] = grads
+        res["loss_rel_err"] = float(f"{abs(loss.item() - float(ref['loss'])) / abs(float(ref['loss'])):.3e}")
+        return res
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 

@@ -64,9 +64,9 @@ SIGNATURES = {
     "cg_raster_debug_fetch": (C.c_int, [C.c_int, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_sample_scratch_bytes": (_sz, [_i64, _i32]),
     "cg_sample_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cg_sample_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_sample_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cg_activate_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cg_activate_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp] + [_vp] * 9),
+    "cg_activate_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp] + [_vp] * 8 + [_i32, _vp]),
     "cg_ssim_fwd": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_ssim_bwd": (C.c_int, [_i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_edge_ssim_loss_stats_bytes": (_sz, []),

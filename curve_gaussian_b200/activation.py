@@ -38,6 +38,9 @@ class _CurveActivate(torch.autograd.Function):
         ctx.meta = (B, n, float(mask_thr), tuple(opacity_logit.shape),
                     tuple(mask_logit.shape) if mask_logit is not None else None)
         ctx.set_materialize_grads(False)
+        from .sampling import direct_target
+        ctx.direct = (opacity_logit, mask_logit) if (direct_target(opacity_logit) and
+                                                     (mask_logit is None or direct_target(mask_logit))) else None
         return rot_n, opacity, scales, all_map
 
     @staticmethod
@@ -51,15 +54,23 @@ class _CurveActivate(torch.autograd.Function):
         g_rot_n, g_opacity, g_scales, g_all_map = c(g_rot_n), c(g_opacity), c(g_scales), c(g_all_map)
         g_rot = torch.empty((P, 4), dtype=torch.float32, device=dev)
         g_scaling = torch.empty((P, 3), dtype=torch.float32, device=dev)
-        g_ol = torch.empty((B,), dtype=torch.float32, device=dev)
-        g_ml = torch.empty((P,), dtype=torch.float32, device=dev) if ml_shape is not None else None
+        from .sampling import direct_grad
+        direct = ctx.direct is not None and all(p is None or direct_grad(p) is not None for p in ctx.direct)
+        if direct:
+            g_ol = direct_grad(ctx.direct[0])
+            g_ml = direct_grad(ctx.direct[1]) if ml_shape is not None else None
+        else:
+            g_ol = torch.empty((B,), dtype=torch.float32, device=dev)
+            g_ml = torch.empty((P,), dtype=torch.float32, device=dev) if ml_shape is not None else None
         with _lib.on_device(dev):
             _lib.check(lib.cg_activate_bwd(B, n, _lib.ptr(xyz_), _lib.ptr(rot_), _lib.ptr(scal_), _lib.ptr(ol_),
                                            _lib.ptr(ml_) if ml_shape is not None else None, thr, _lib.ptr(cam_),
                                            _lib.ptr(vm_), _lib.ptr(g_rot_n), _lib.ptr(g_opacity), _lib.ptr(g_scales),
                                            _lib.ptr(g_all_map), _lib.ptr(g_rot), _lib.ptr(g_scaling), _lib.ptr(g_ol),
-                                           _lib.ptr(g_ml), _lib.stream(dev)),
+                                           _lib.ptr(g_ml), 1 if direct else 0, _lib.stream(dev)),
                        "cg_activate_bwd")
+        if direct:
+            return (None, g_rot, g_scaling, None, None, None, None, None, None)
         return (None, g_rot, g_scaling, g_ol.view(ol_shape), g_ml.view(ml_shape) if g_ml is not None else None,
                 None, None, None, None)
 

@@ -53,7 +53,7 @@ activate_bwd_point(int64_t P, int n, const float* __restrict__ xyz, const float*
                    const float* __restrict__ mask_logit, float mask_thr, const float* __restrict__ campos,
                    const float* __restrict__ vm, const float* __restrict__ g_rot_n, const float* __restrict__ g_opacity,
                    const float* __restrict__ g_scales, const float* __restrict__ g_all_map,
-                   float* __restrict__ g_rot, float* __restrict__ g_scaling, float* __restrict__ g_mask_logit) {
+                   float* __restrict__ g_rot, float* __restrict__ g_scaling, float* __restrict__ g_mask_logit, int accumulate) {
   pdl_wait();
   const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (g >= P) return;
@@ -70,7 +70,8 @@ activate_bwd_point(int64_t P, int n, const float* __restrict__ xyz, const float*
     const float go = g_opacity ? g_opacity[g] : 0.f;
     const float op = sigmoidf_(opacity_logit[g / n]);
     const float gm = go * op + gs0 * scaling[3 * g] + gs1 * scaling[3 * g + 1] + gs2 * scaling[3 * g + 2];
-    g_mask_logit[g] = gm * sm * (1.f - sm);
+    const float gml = gm * sm * (1.f - sm);
+    g_mask_logit[g] = accumulate ? g_mask_logit[g] + gml : gml;
   }
   // ---- rotation
   const float4 q = reinterpret_cast<const float4*>(rot)[g];
@@ -111,7 +112,7 @@ activate_bwd_point(int64_t P, int n, const float* __restrict__ xyz, const float*
 
 __global__ void __launch_bounds__(256)
 activate_bwd_curve(int64_t B, int n, const float* __restrict__ opacity_logit, const float* __restrict__ mask_logit,
-                   float mask_thr, const float* __restrict__ g_opacity, float* __restrict__ g_opacity_logit) {
+                   float mask_thr, const float* __restrict__ g_opacity, float* __restrict__ g_opacity_logit, int accumulate) {
   pdl_wait();
   const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,7 +131,10 @@ activate_bwd_curve(int64_t B, int n, const float* __restrict__ opacity_logit, co
   }
   for (int o = 16; o > 0; o >>= 1) g_op_sum += __shfl_xor_sync(0xffffffffu, g_op_sum, o);
   const float op = sigmoidf_(opacity_logit[b]);
-  if (lane == 0) g_opacity_logit[b] = g_op_sum * op * (1.f - op);
+  if (lane == 0) {
+    const float gol = g_op_sum * op * (1.f - op);
+    g_opacity_logit[b] = accumulate ? g_opacity_logit[b] + gol : gol;
+  }
 }
 
 }  // namespace cg
@@ -162,7 +166,7 @@ int cg_activate_bwd(int64_t B, int32_t n, const float* xyz, const float* rotatio
                     const float* opacity_logit, const float* mask_logit, float mask_thr, const float* campos,
                     const float* viewmatrix, const float* g_rot_n, const float* g_opacity, const float* g_scales,
                     const float* g_all_map, float* g_rotation, float* g_scaling, float* g_opacity_logit,
-                    float* g_mask_logit, void* stream) {
+                    float* g_mask_logit, int32_t accumulate, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (B == 0) return CG_OK;
   CG_ARG(B > 0 && n > 0, "B/n");
@@ -173,10 +177,10 @@ int cg_activate_bwd(int64_t B, int32_t n, const float* xyz, const float* rotatio
   StageTimer t_(ST_ACTIVATE_BWD, st, 2);
   launch_k(activate_bwd_point, dim3(unsigned((P + 255) / 256)), dim3(256), 0, st, P, n, xyz, rotation, scaling, opacity_logit, mask_logit,
                                                                mask_thr, campos, viewmatrix, g_rot_n, g_opacity, g_scales,
-                                                               g_all_map, g_rotation, g_scaling, g_mask_logit);
+                                                               g_all_map, g_rotation, g_scaling, g_mask_logit, int(accumulate));
   CG_LAUNCH_CHECK(0, st);
   launch_k(activate_bwd_curve, dim3(unsigned((B * 32 + 255) / 256)), dim3(256), 0, st, B, n, opacity_logit, mask_logit, mask_thr,
-                                                                    g_opacity, g_opacity_logit);
+                                                                    g_opacity, g_opacity_logit, int(accumulate));
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }

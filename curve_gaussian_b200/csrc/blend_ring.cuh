@@ -38,9 +38,13 @@ constexpr int RING_WARPS = 4;     // per CTA; warps are independent
 #define CG_RING_UNROLL 1
 #endif
 constexpr int RING_UNROLL = CG_RING_UNROLL;   // steps per loop iteration
-constexpr int RING_NB = 2;        // blocks that may start within one epoch
+#ifndef CG_RING_NB
+#define CG_RING_NB 2
+#endif
+constexpr int RING_NB = CG_RING_NB;   // blocks that may start within one epoch (each needs a pixel table)
 constexpr int RING_TSLOTS = 3 * RING_NB;
-constexpr uint32_t RING_POS_MASK = 0x0fffffffu;   // list position within the tile; bits 28-30 table slot, bit 31 first-of-block
+constexpr uint32_t RING_POS_MASK = 0x07ffffffu;   // list position within the tile; bits 27-30 table slot, bit 31 first-of-block
+static_assert(RING_TSLOTS <= 16, "table slot field is 4 bits");
 
 struct __align__(16) RingWarp {
   // (the quads are chosen so that every vector load / store of the per-step switch moves whole register quads:
@@ -134,8 +138,10 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   // assignment of epoch E: which list entry each lane takes; a_addr = index into cand (or ~0), a_flag = first|slot bits.
   // At most RING_NB blocks start per epoch (they need a pixel table each); empty blocks are skipped. An epoch
   // without any element therefore means that the warp has run out of blocks.
-  auto assign = [&](int E, uint32_t& a_addr, uint32_t& a_flag, uint32_t& nb0, uint32_t& nb1) -> uint32_t {
-    a_addr = 0xffffffffu; a_flag = 0; nb0 = nb1 = 0xffffffffu;
+  auto assign = [&](int E, uint32_t& a_addr, uint32_t& a_flag, uint32_t (&nb)[RING_NB]) -> uint32_t {
+    a_addr = 0xffffffffu; a_flag = 0;
+#pragma unroll
+    for (int k = 0; k < RING_NB; ++k) nb[k] = 0xffffffffu;
     uint32_t taken = min(cb_rem, 32u);
     if (lane < taken) a_addr = cb_base + (cb_rem - 1u - lane);
     cb_rem -= taken;
@@ -153,9 +159,10 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
           const uint32_t n = min(cnt, 32u - taken);
           if (lane >= taken && lane < taken + n) {
             a_addr = base + (cnt - 1u - (lane - taken));
-            if (lane == taken) a_flag = 0x80000000u | (uint32_t((E % 3) * RING_NB + started) << 28);
+            if (lane == taken) a_flag = 0x80000000u | (uint32_t((E % 3) * RING_NB + started) << 27);
           }
-          if (started == 0) nb0 = bid; else nb1 = bid;
+#pragma unroll
+          for (int k = 0; k < RING_NB; ++k) if (k == started) nb[k] = bid;
           ++started;
           cb_rem = cnt - n; cb_base = base;
           taken += n;
@@ -175,7 +182,10 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   float spad = 0.f;   // fourth register of the {S4, S5, S7, -} quad the switch stores with one vector store
 
   // epoch bookkeeping: A = epoch m+1 (positions loaded, records not yet), B = epoch m+2 (being assigned)
-  uint32_t posA = 0, idA = 0, flagA = 0, nbA0 = 0xffffffffu, nbA1 = 0xffffffffu, validA = 0;
+  uint32_t posA = 0, idA = 0, flagA = 0, validA = 0;
+  uint32_t nbA[RING_NB];
+#pragma unroll
+  for (int k = 0; k < RING_NB; ++k) nbA[k] = 0xffffffffu;
   uint32_t posw_pending = RING_POS_MASK;     // position|flags word of this lane's element of the next epoch
   uint32_t real_m2 = 0, real_m1 = 0, real_0 = 0, real_p1 = 0;   // real elements of epochs m-2, m-1, m, m+1
 
@@ -217,7 +227,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
         }
 #pragma unroll
         for (int k = 0; k < RING_NB; ++k) {
-          const uint32_t nb = k == 0 ? nbA0 : nbA1;
+          const uint32_t nb = nbA[k];
           if (nb != 0xffffffffu) {
             const int ts = (E % 3) * RING_NB + k;
             const uint32_t tile = nb >> 3, b = nb & 7u;
@@ -239,12 +249,12 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     }
     {
       // assignment of epoch m+2 and its candidate positions (consumed at the next boundary)
-      uint32_t a_addr, a_flag, nb0, nb1;
-      const uint32_t real_p2 = assign(m + 2, a_addr, a_flag, nb0, nb1);
+      uint32_t a_addr, a_flag;
+      const uint32_t real_p2 = assign(m + 2, a_addr, a_flag, nbA);
       validA = a_addr != 0xffffffffu;
       posA = validA ? cand[a_addr] : 0u;
       idA = validA ? cand_id[a_addr] : 0u;
-      flagA = a_flag; nbA0 = nb0; nbA1 = nb1;
+      flagA = a_flag;
       real_m2 = real_m1; real_m1 = real_0; real_0 = real_p1; real_p1 = real_p2;
     }
     if (m < 0) continue;
@@ -284,7 +294,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       const uint32_t posw = __float_as_uint(poswf);
       if (posw & 0x80000000u) {
         // first element of its block (back to front): the arriving slot becomes pixel p of that block
-        const uint32_t ts = (posw >> 28) & 7u, p = (u - lane) & 31u;
+        const uint32_t ts = (posw >> 27) & 15u, p = (u - lane) & 31u;
         T = rw.tT[ts][p];
         Tf = T;
         dLp = rw.tD[ts][p];

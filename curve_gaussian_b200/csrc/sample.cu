@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256)
 sample_bwd_curve(int64_t B, int n, const float* __restrict__ width, const uint8_t* __restrict__ is_bezier,
                  const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
                  const double* __restrict__ sums, const float* __restrict__ pt, const float* __restrict__ dL_dscaling,
-                 float* __restrict__ dL_dcp, float* __restrict__ dL_dwidth) {
+                 float* __restrict__ dL_dcp, float* __restrict__ dL_dwidth, int accumulate) {
   pdl_wait();
   const int64_t b = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -352,8 +352,9 @@ sample_bwd_curve(int64_t B, int n, const float* __restrict__ width, const uint8_
     for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) dL_dcp[b * 12 + i] = acc[i];
-    dL_dwidth[b] = acc[12] * expf(width[b]);
+    for (int i = 0; i < 12; ++i) dL_dcp[b * 12 + i] = accumulate ? dL_dcp[b * 12 + i] + acc[i] : acc[i];
+    const float gw = acc[12] * expf(width[b]);
+    dL_dwidth[b] = accumulate ? dL_dwidth[b] + gw : gw;
   }
 }
 
@@ -393,7 +394,7 @@ int cg_sample_fwd(int64_t B, int32_t n, const float* curve_points, const float* 
 int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* width, const uint8_t* is_bezier,
                   const float* t, float half_step, const float* norms, const float* dL_dxyz,
                   const float* dL_drotation, const float* dL_dscaling, float* dL_dcurve_points, float* dL_dwidth,
-                  void* scratch, void* stream) {
+                  void* scratch, int32_t accumulate, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (B == 0) return CG_OK;
   CG_ARG(B > 0 && n > 0, "B/n");
@@ -408,7 +409,7 @@ int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* 
                                                              dL_drotation, dL_dscaling, pt, sums);
   CG_LAUNCH_CHECK(0, st);
   launch_k(sample_bwd_curve, dim3(unsigned((B * 32 + 255) / 256)), dim3(256), 0, st, B, n, width, is_bezier, t, half_step, norms, sums, pt,
-                                                                  dL_dscaling, dL_dcurve_points, dL_dwidth);
+                                                                  dL_dscaling, dL_dcurve_points, dL_dwidth, int(accumulate));
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }

@@ -27,8 +27,18 @@ CURVE_KEYS = ("curve_points", "width", "mask", "is_bezier", "n_gaussians")
 def capture(model) -> tuple:
     """(the reference's 12 entries ..., curve dict). Index 12 is ours."""
     opt = model.optimizer.state_dict() if getattr(model, "optimizer", None) is not None else None
+    if getattr(model, "_curve_points", None) is not None and model._curve_points.is_cuda and hasattr(model, "prepare_scaling_rot"):
+        # a graph-mode loop re-samples inside its captured step only: make the sampled tensors saved below belong to
+        # the curve parameters saved next to them
+        with torch.no_grad():
+            model.prepare_scaling_rot()
+    params = ("_curve_points", "_width", "_opacity", "_mask", "_features_dc", "_features_rest")
     curves = {"curve_points": model._curve_points, "width": model._width, "mask": model._mask,
-              "is_bezier": model.is_bezier, "n_gaussians": model.n_gaussians}
+              "is_bezier": model.is_bezier, "n_gaussians": model.n_gaussians,
+              # which parameters were trainable (fix_opacity() freezes _opacity), and the per-image exposure state
+              "requires_grad": {k: bool(getattr(model, k).requires_grad) for k in params if hasattr(model, k)},
+              "exposure": getattr(model, "_exposure", None),
+              "exposure_mapping": dict(getattr(model, "exposure_mapping", {}) or {})}
     return (model.active_sh_degree, model._xyz, model._features_dc, model._features_rest, model._scaling,
             model._rotation, model._opacity, model.max_radii2D, model.xyz_gradient_accum, model.denom, opt,
             model.spatial_lr_scale, curves)
@@ -43,9 +53,15 @@ def restore(model, model_args, training_args=None) -> None:
     if int(curves["n_gaussians"]) != int(model.n_gaussians):
         raise ValueError(f"checkpoint samples {curves['n_gaussians']} Gaussians per curve, the model {model.n_gaussians}")
     dev = model.sample_t.device
-    P = lambda t: nn.Parameter(t.detach().to(dev).clone().requires_grad_(True))
-    model._curve_points, model._width, model._mask = P(curves["curve_points"]), P(curves["width"]), P(curves["mask"])
-    model._opacity, model._features_dc, model._features_rest = P(opacity), P(f_dc), P(f_rest)
+    rg = curves.get("requires_grad", {})
+    P = lambda t, k: nn.Parameter(t.detach().to(dev).clone().requires_grad_(bool(rg.get(k, True))))
+    model._curve_points, model._width = P(curves["curve_points"], "_curve_points"), P(curves["width"], "_width")
+    model._mask = P(curves["mask"], "_mask")
+    model._opacity, model._features_dc = P(opacity, "_opacity"), P(f_dc, "_features_dc")
+    model._features_rest = P(f_rest, "_features_rest")
+    if curves.get("exposure") is not None:
+        model._exposure = nn.Parameter(curves["exposure"].detach().to(dev).clone().requires_grad_(True))
+        model.exposure_mapping = dict(curves.get("exposure_mapping", {}))
     model.is_bezier = curves["is_bezier"].to(dev).bool().clone()
     model.max_radii2D = max_radii2D.to(dev).clone()
     model.prepare_scaling_rot()          # _xyz/_rotation/_scaling are functions of the curve parameters

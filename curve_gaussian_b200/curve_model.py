@@ -95,6 +95,13 @@ class GaussianCurveModel(CurveTopology):
         self.spatial_lr_scale = spatial_lr_scale
         dev = self.sample_t.device
         self.create_from_points(torch.as_tensor(np.asarray(pcd.points)).float(), init_size)
+        colors = getattr(pcd, "colors", None)
+        if colors is not None and len(colors) == self._curve_points.shape[0]:
+            # RGB2SH of the first colour channel, repeated over the curve's samples (:158-166): only read back by the
+            # PLY / checkpoint writers (render() draws every Gaussian with colour 1)
+            c0 = torch.as_tensor(np.asarray(colors))[:, 0:1].float().to(dev)
+            dc = ((c0 - 0.5) / 0.28209479177387814)[:, None, :, None].repeat(1, self.n_gaussians, 1, 1)
+            self._features_dc = nn.Parameter(dc.contiguous().requires_grad_(True))
         names = [getattr(c, "image_name", str(i)) for i, c in enumerate(cam_infos)] if not isinstance(cam_infos, int) \
             else [str(i) for i in range(cam_infos)]
         self.exposure_mapping = {name: i for i, name in enumerate(names)}

@@ -56,10 +56,16 @@ def balanced_view_partition(costs: Sequence[float], world: int) -> List[List[int
 
 
 class FlatGrad:
-    """One contiguous gradient buffer behind several parameters."""
+    """One contiguous gradient buffer behind several parameters.
 
-    def __init__(self, params: Iterable[torch.Tensor]):
+    direct=True additionally lets the library's backward kernels ADD their curve-parameter gradients straight into
+    this buffer (sampling.py / activation.py check the flag): no AccumulateGrad node runs for these parameters, so a
+    step costs neither the ATen add / fill kernels nor - inside a CUDA-graph capture - a node bound to another stream.
+    The buffer must then be zeroed by the caller before every accumulation round (zero()), as with any .grad."""
+
+    def __init__(self, params: Iterable[torch.Tensor], direct: bool = False):
         self.params = [p for p in params]
+        self.direct = bool(direct)
         if not self.params:
             raise ValueError("no parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
@@ -74,6 +80,7 @@ class FlatGrad:
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            p._cg_direct_grad = self.direct
             off += p.numel()
 
     def zero(self) -> None:

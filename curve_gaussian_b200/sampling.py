@@ -18,6 +18,19 @@ def sample_t(n: int, device) -> torch.Tensor:
     return torch.linspace(0.5 / n, 1 - 0.5 / n, n, device=device)
 
 
+def direct_target(p) -> bool:
+    """Is `p` a leaf parameter bound to a FlatGrad(direct=True) buffer (parallel.py)?"""
+    return bool(getattr(p, "_cg_direct_grad", False)) and p.is_leaf and p.requires_grad
+
+
+def direct_grad(p):
+    """The gradient buffer a backward kernel may add into, or None (then the gradient is returned to autograd)."""
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape or g.device != p.device:
+        return None
+    return g
+
+
 class _CurveSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, curve_points, width, is_bezier, t):
@@ -45,6 +58,9 @@ class _CurveSample(torch.autograd.Function):
                        "cg_sample_fwd")
         ctx.save_for_backward(cp, w, isb if isb is not None else torch.empty(0, device=dev), tt, norms)
         ctx.shape = (B, n, half_step, tuple(width.shape))
+        # parameters whose .grad is a view of a FlatGrad(direct=True) buffer get their gradient ADDED there by the
+        # backward kernel itself (no AccumulateGrad node, no ATen add / fill kernels): see parallel.FlatGrad
+        ctx.direct = (curve_points, width) if (direct_target(curve_points) and direct_target(width)) else None
         ctx.set_materialize_grads(False)
         return xyz, rot, scaling
 
@@ -54,16 +70,22 @@ class _CurveSample(torch.autograd.Function):
         cp, w, isb, tt, norms = ctx.saved_tensors
         B, n, half_step, wshape = ctx.shape
         dev = cp.device
-        g_cp = torch.empty((B, 4, 3), dtype=torch.float32, device=dev)
-        g_w = torch.empty((B,), dtype=torch.float32, device=dev)
+        direct = ctx.direct is not None and all(direct_grad(p) is not None for p in ctx.direct)
+        if direct:
+            g_cp, g_w = direct_grad(ctx.direct[0]), direct_grad(ctx.direct[1])
+        else:
+            g_cp = torch.empty((B, 4, 3), dtype=torch.float32, device=dev)
+            g_w = torch.empty((B,), dtype=torch.float32, device=dev)
         scratch = torch.empty(max(lib.cg_sample_scratch_bytes(B, n), 8), dtype=torch.uint8, device=dev)
         c = lambda g: None if g is None else g.float().contiguous()
         g_xyz, g_rot, g_scaling = c(g_xyz), c(g_rot), c(g_scaling)
         with _lib.on_device(dev):
             _lib.check(lib.cg_sample_bwd(B, n, _lib.ptr(cp), _lib.ptr(w), _lib.ptr(isb), _lib.ptr(tt), half_step,
                                          norms.data_ptr(), _lib.ptr(g_xyz), _lib.ptr(g_rot), _lib.ptr(g_scaling),
-                                         _lib.ptr(g_cp), _lib.ptr(g_w), scratch.data_ptr(),
+                                         _lib.ptr(g_cp), _lib.ptr(g_w), scratch.data_ptr(), 1 if direct else 0,
                                          _lib.stream(dev)), "cg_sample_bwd")
+        if direct:
+            return None, None, None, None
         return g_cp, g_w.view(wshape), None, None
 
 

@@ -223,7 +223,7 @@ class TrainLoop:
             self._gt.copy_(gt)
             body()
             reached = [p for p in params if p.grad is not None]
-            self._fg = FlatGrad(reached)
+            self._fg = FlatGrad(reached, direct=True)
 
             def fn():
                 self._fg.zero()

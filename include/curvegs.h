@@ -200,7 +200,10 @@ int cg_sample_bwd(int64_t B, int32_t n, const float* curve_points, const float* 
                   const float* norms,
                   const float* dL_dxyz, const float* dL_drotation, const float* dL_dscaling,
                   float* dL_dcurve_points, float* dL_dwidth,
-                  void* scratch, void* stream);
+                  void* scratch,
+                  int32_t accumulate,   /* != 0: ADD into dL_dcurve_points / dL_dwidth (the caller's gradient
+                                           buffers) instead of overwriting them */
+                  void* stream);
 
 /* Per-view activations render() applies before rasterizing
  * (gaussian_renderer/__init__.py:57-104, scene/gaussian_curve_model.py:99-122):
@@ -219,6 +222,7 @@ int cg_activate_bwd(int64_t B, int32_t n, const float* xyz, const float* rotatio
                     const float* campos, const float* viewmatrix,
                     const float* g_rot_n, const float* g_opacity, const float* g_scales, const float* g_all_map,
                     float* g_rotation, float* g_scaling, float* g_opacity_logit, float* g_mask_logit,
+                    int32_t accumulate,   /* != 0: ADD into g_opacity_logit / g_mask_logit instead of overwriting */
                     void* stream);
 
 /* ------------------------------------------------------------------ */

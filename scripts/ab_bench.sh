@@ -12,7 +12,7 @@ if [ "${2:-}" != "skip-tests" ]; then
 fi
 run() {
   local name=$1; shift
-  timeout -k 10 200 env "$@" python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $OUT/bench_$name.json 2> $OUT/bench_$name.err
+  timeout -k 10 200 env "$@" python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-small-scene --no-reference-step > $OUT/bench_$name.json 2> $OUT/bench_$name.err
   python - "$OUT/bench_$name.json" "$name" <<'PY'
 import json, sys
 try:

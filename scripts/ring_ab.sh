@@ -8,7 +8,7 @@ if [ "${2:-}" != "skip-tests" ]; then
   tail -15 $OUT/pytest.log
 fi
 for v in 1 0; do
-  CURVEGS_BWD_RING=$v timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-small-scene > $OUT/bench_ring$v.json 2> $OUT/bench_ring$v.err
+  CURVEGS_BWD_RING=$v timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-small-scene --no-reference-step > $OUT/bench_ring$v.json 2> $OUT/bench_ring$v.err
   python - "$OUT/bench_ring$v.json" "$v" <<'PY'
 import json, sys
 try:

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-for name in ("bench.json", "bench_reference.json"):
+for name in ("bench.json", "bench_reference.json", "sass_excerpt.txt", "cub_sort_yardstick.txt"):
     f = os.path.join(src, name)
     if os.path.exists(f) and os.path.getsize(f):
         shutil.copy(f, os.path.join(P, f"{prefix}_{name}"))
@@ -70,7 +70,8 @@ if os.path.exists(rep):
     units = dict(zip(hdr, rows[1]))
     traffic = {}
     limiters = {}     # per stage: what ncu says keeps the kernel busy (read by bench.py next to roofline.traffic)
-    stage_of = {"blend_bwd": "blend_bwd", "blend_fwd": "blend_fwd", "gather_records": "gather_records",
+    stage_of = {"blend_bwd": "blend_bwd", "blend_bwd_ring": "blend_bwd", "blend_fwd": "blend_fwd",
+                "tile_ranges": "tile_ranges", "emit_keys": "emit_keys",
                 "preprocess_fwd": "preprocess_fwd", "preprocess_bwd": "preprocess_bwd"}
     seen = collections.Counter()
     with open(os.path.join(P, f"{prefix}_ncu_full_summary.txt"), "w") as f:
@@ -94,7 +95,9 @@ if os.path.exists(rep):
                         "issue_active_pct": round(float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]), 1),
                         "dram_pct_of_peak": round(float(d["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]), 1),
                         "warps_active_pct": round(float(d["sm__warps_active.avg.pct_of_peak_sustained_active"]), 1),
-                        "registers": int(float(d["launch__registers_per_thread"]))}
+                        "registers": int(float(d["launch__registers_per_thread"])),
+                        "inst_executed": int(float(d["smsp__inst_executed.sum"])),
+                        "source": f"profiles/{prefix}_ncu_full_summary.txt"}
                 if base == "sort_onesweep_pass":
                     traffic["radix_sort"] = traffic.get("radix_sort", 0) + int(mb * scale)
             except Exception:

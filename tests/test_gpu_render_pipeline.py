@@ -118,3 +118,33 @@ def test_empty_and_degenerate_inputs(cuda_dev):
         r(means3D=m, means2D=z(5, 3), opacities=z(5, 1))
     vis = r.markVisible(m)
     assert vis.dtype == torch.bool and not bool(vis.any())
+
+
+def test_direct_gradient_accumulation_equals_autograd(cuda_dev):
+    """FlatGrad(direct=True): the sampling / activation backward kernels add their curve-parameter gradients straight
+    into the flat buffer. Same numbers as the AccumulateGrad path, over two accumulated views, mask included."""
+    from curve_gaussian_b200.loss import edge_ssim_loss
+    from curve_gaussian_b200.parallel import FlatGrad
+    dev = cuda_dev
+    B, n, W, H = 120, 16, 256, 192
+    cp, width, opl, isb = synth.random_curves(B, seed=31, line_fraction=0.3)
+    width = width + 0.6
+    mask = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(8)) * 3
+    cams = [c.to(dev) for c in synth.random_cameras(2, W, H, seed=32)]
+    gts = [(torch.rand(1, H, W, generator=torch.Generator().manual_seed(40 + i)) > 0.9).float().to(dev) for i in range(2)]
+    bg = torch.zeros(3, device=dev)
+    flats = []
+    for direct in (False, True):
+        m = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb, mask)
+        fg = FlatGrad([m._curve_points, m._width, m._opacity, m._mask], direct=direct)
+        fg.zero()
+        for cam, gt in zip(cams, gts):
+            m.prepare_scaling_rot()
+            pkg = render(cam, m, Pipe(), bg, use_mask=True, mask_thr=0.01)
+            edge_ssim_loss(pkg["render_raw"], gt, clamp=True).backward()
+        torch.cuda.synchronize()
+        assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in fg.params), "a .grad was replaced"
+        flats.append(fg.flat.clone())
+    assert flats[0].abs().max() > 0
+    err = ((flats[0] - flats[1]).abs().max() / flats[0].abs().max()).item()
+    assert err <= 1e-6, err    # only the rasterizer's atomics order differs between the two runs
