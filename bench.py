@@ -488,9 +488,28 @@ def small_scene_step(dev, pipe, B=417, n=12, W=800, H=800, steps=60, nviews=8):
             return gs.replay()
 
         graph_ms = timed(graphed)
-        return {"workload": f"{B} curves x {n} samples = {B * n} curve-Gaussians, {W}x{H}, {nviews} views",
-                "eager_ms_per_step": round(eager_ms, 4), "graph_ms_per_step": round(graph_ms, 4),
-                "graph_views_per_s": round(1e3 / graph_ms, 1), "verified_no_capacity_overflow": bool(gs.verify())}
+        res = {"workload": f"{B} curves x {n} samples = {B * n} curve-Gaussians, {W}x{H}, {nviews} views",
+               "eager_ms_per_step": round(eager_ms, 4), "graph_ms_per_step": round(graph_ms, 4),
+               "graph_views_per_s": round(1e3 / graph_ms, 1), "verified_no_capacity_overflow": bool(gs.verify())}
+        # all nviews views in flight at once: the captured step replayed concurrently on nviews streams
+        try:
+            from curve_gaussian_b200.graph import MultiViewStep
+
+            def body1(cam, gt):
+                model.prepare_scaling_rot()
+                loss = edge_ssim_loss(render(cam, model, pipe, bg)["render_raw"], gt, clamp=True)
+                loss.backward()
+                return loss
+
+            mv = MultiViewStep([model._curve_points, model._width, model._opacity, model._mask], body1, cams[0], gts[0],
+                               nviews).capture(cams[:2])
+            mv_ms = timed(lambda i: mv.replay(cams, gts))          # one call = nviews views
+            res["multi_view_graph_ms_per_view"] = round(mv_ms / nviews, 4)
+            res["multi_view_graph_views_per_s"] = round(nviews * 1e3 / mv_ms, 1)
+            res["multi_view_verified_no_capacity_overflow"] = bool(mv.verify())
+        except Exception as e:
+            res["multi_view_error"] = f"{type(e).__name__}: {e}"[:200]
+        return res
     except Exception as e:   # informational only: never take the headline line down with it
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 

@@ -13,7 +13,8 @@ from . import _lib
 
 class _CurveActivate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, rotation, scaling, opacity_logit, mask_logit, n, mask_thr, campos, viewmatrix):
+    def forward(ctx, xyz, rotation, scaling, opacity_logit, mask_logit, n, mask_thr, campos, viewmatrix,
+                direct_params=None):
         lib = _lib.load()
         if not xyz.is_cuda:
             raise _lib.CurveGSError("activation needs CUDA tensors; there is no CPU path")
@@ -38,9 +39,7 @@ class _CurveActivate(torch.autograd.Function):
         ctx.meta = (B, n, float(mask_thr), tuple(opacity_logit.shape),
                     tuple(mask_logit.shape) if mask_logit is not None else None)
         ctx.set_materialize_grads(False)
-        from .sampling import direct_target
-        ctx.direct = (opacity_logit, mask_logit) if (direct_target(opacity_logit) and
-                                                     (mask_logit is None or direct_target(mask_logit))) else None
+        ctx.direct = direct_params     # (opacity, mask) parameter objects when they arrived detached: curve_activate
         return rot_n, opacity, scales, all_map
 
     @staticmethod
@@ -56,6 +55,9 @@ class _CurveActivate(torch.autograd.Function):
         g_scaling = torch.empty((P, 3), dtype=torch.float32, device=dev)
         from .sampling import direct_grad
         direct = ctx.direct is not None and all(p is None or direct_grad(p) is not None for p in ctx.direct)
+        if ctx.direct is not None and not direct:
+            raise _lib.CurveGSError("a parameter's FlatGrad(direct=True) gradient buffer was replaced between forward and "
+                                    "backward (call FlatGrad.bind() after an optimizer step that set .grad to None)")
         if direct:
             g_ol = direct_grad(ctx.direct[0])
             g_ml = direct_grad(ctx.direct[1]) if ml_shape is not None else None
@@ -70,13 +72,21 @@ class _CurveActivate(torch.autograd.Function):
                                            _lib.ptr(g_ml), 1 if direct else 0, _lib.stream(dev)),
                        "cg_activate_bwd")
         if direct:
-            return (None, g_rot, g_scaling, None, None, None, None, None, None)
+            return (None, g_rot, g_scaling, None, None, None, None, None, None, None)
         return (None, g_rot, g_scaling, g_ol.view(ol_shape), g_ml.view(ml_shape) if g_ml is not None else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def curve_activate(xyz, rotation, scaling, opacity_logit, mask_logit, n, campos, viewmatrix, use_mask=False,
                    mask_thr=0.01):
     """-> rotations (P,4) unit, opacity (P,1), scales (P,3), all_map (P,4)."""
-    return _CurveActivate.apply(xyz, rotation, scaling, opacity_logit, mask_logit if use_mask else None, int(n),
-                                float(mask_thr), campos, viewmatrix)
+    from .sampling import direct_grad, direct_target
+    ml = mask_logit if use_mask else None
+    if torch.is_grad_enabled() and direct_target(opacity_logit) and direct_grad(opacity_logit) is not None and \
+            (ml is None or (direct_target(ml) and direct_grad(ml) is not None)) and \
+            (rotation.requires_grad or scaling.requires_grad):
+        # direct mode (parallel.FlatGrad(direct=True)): the parameters go in detached and the backward kernel adds
+        # their gradients into .grad itself - no edge to their AccumulateGrad nodes (see sampling.sample_curves)
+        return _CurveActivate.apply(xyz, rotation, scaling, opacity_logit.detach(), ml.detach() if ml is not None else None,
+                                    int(n), float(mask_thr), campos, viewmatrix, (opacity_logit, ml))
+    return _CurveActivate.apply(xyz, rotation, scaling, opacity_logit, ml, int(n), float(mask_thr), campos, viewmatrix)

@@ -146,3 +146,98 @@ class GraphedStep:
             self.graph = None
             self.capture()
             return False
+
+
+class MultiViewStep:
+    """V views of one training step in flight at once (the small-scene half).
+
+    At the reference's own scene sizes (5 k - 100 k curve-Gaussians) one captured step is a chain of ~45 kernels of a
+    few microseconds each: a single replay keeps a handful of the 148 SMs busy and is bound by the latency of the
+    chain, not by work. Here the SAME step is captured V times - each copy with its own camera slot, target image,
+    rasterizer state and gradient buffer - and the V graphs are replayed concurrently on V streams, so the chains of
+    different views interleave on the GPU. Every copy computes exactly what a single `GraphedStep` computes for its
+    view (same kernels, same launch geometry: per-view results are bit-identical); the copies' curve-parameter
+    gradients are rows of one (V, n) buffer and are summed into the parameters' `.grad` after the replays, which is
+    the multi-view accumulation of `parallel.FlatGrad` with the views running side by side instead of one after the
+    other.
+
+    body(cam, gt) -> loss runs one view: it must call `model.prepare_scaling_rot()`, `render(cam, ...)`, a loss and
+    `.backward()`, reading the view from `cam` (a StaticCamera) and `gt` (a fixed tensor).
+    """
+
+    def __init__(self, params: Sequence[torch.Tensor], body: Callable[[StaticCamera, torch.Tensor], torch.Tensor],
+                 like_cam, like_gt: torch.Tensor, views: int):
+        self.params = list(params)
+        self.V = int(views)
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flats = torch.zeros(self.V, n, dtype=self.params[0].dtype, device=dev)
+        self.total = torch.zeros(n, dtype=self.params[0].dtype, device=dev)
+        self.scams = [StaticCamera(like_cam) for _ in range(self.V)]
+        self.gts = [torch.empty_like(like_gt) for _ in range(self.V)]
+        self.streams = [torch.cuda.Stream(dev) for _ in range(self.V)]
+        self.steps = []
+        for k in range(self.V):
+            def fn(k=k):
+                self.flats[k].zero_()
+                return body(self.scams[k], self.gts[k])
+            self.steps.append(GraphedStep(fn))
+        # all copies warm up and capture on ONE side stream: autograd remembers, per parameter, the stream its
+        # AccumulateGrad node was created on and makes every backward wait for it - from a capture on any other stream
+        # that is a dependency on uncaptured work (cudaErrorStreamCaptureIsolation). A graph does not remember the
+        # stream it was captured on, so the copies still replay on V different streams.
+        side = torch.cuda.Stream(dev)
+        for step in self.steps:
+            step._side = side
+
+    def _bind(self, flat: torch.Tensor) -> None:
+        off = 0
+        for p in self.params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            p._cg_direct_grad = True      # the library's backward kernels add straight into the bound buffer
+            off += p.numel()
+
+    def capture(self, calibrate_cams: Sequence = ()) -> "MultiViewStep":
+        """Capture the V copies, one after the other; `calibrate_cams`: views that show the binning policy of every
+        copy the largest tile-instance count it will meet."""
+        for k, step in enumerate(self.steps):
+            self._bind(self.flats[k])          # this copy's backward is captured writing into row k
+            step.calibrate = [(lambda c=c, k=k: self.scams[k].load(c)) for c in calibrate_cams]
+            step.capture()
+        self._bind(self.total)                 # what the optimizer sees
+        return self
+
+    def replay(self, cams: Sequence, gts: Sequence[torch.Tensor]):
+        """Run len(cams) <= V views concurrently; returns their (static) loss tensors. Afterwards the parameters'
+        `.grad` (views of `self.total`) hold the SUM of the views' gradients."""
+        nv = len(cams)
+        if nv > self.V or nv != len(gts):
+            raise ValueError(f"{nv} views for {self.V} captured copies")
+        cur = torch.cuda.current_stream()
+        for k in range(nv):
+            self.scams[k].load(cams[k])
+            self.gts[k].copy_(gts[k], non_blocking=True)
+        outs = []
+        for k in range(nv):
+            s = self.streams[k]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                outs.append(self.steps[k].replay())
+        for k in range(nv):
+            cur.wait_stream(self.streams[k])
+        torch.sum(self.flats[:nv], dim=0, out=self.total)
+        return outs
+
+    def verify(self) -> bool:
+        """After a synchronisation: False if a copy overflowed its captured binning capacity (it was re-captured)."""
+        ok = True
+        for k, step in enumerate(self.steps):
+            try:
+                step.policy.check()
+            except _rz.CapacityOverflow:
+                self._bind(self.flats[k])
+                step.graph = None
+                step.capture()
+                self._bind(self.total)
+                ok = False
+        return ok

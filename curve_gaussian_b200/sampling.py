@@ -33,7 +33,7 @@ def direct_grad(p):
 
 class _CurveSample(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, curve_points, width, is_bezier, t):
+    def forward(ctx, curve_points, width, is_bezier, t, anchor=None, direct_params=None):
         lib = _lib.load()
         if not curve_points.is_cuda:
             raise _lib.CurveGSError("curve_points must be a CUDA tensor; there is no CPU path")
@@ -60,7 +60,9 @@ class _CurveSample(torch.autograd.Function):
         ctx.shape = (B, n, half_step, tuple(width.shape))
         # parameters whose .grad is a view of a FlatGrad(direct=True) buffer get their gradient ADDED there by the
         # backward kernel itself (no AccumulateGrad node, no ATen add / fill kernels): see parallel.FlatGrad
-        ctx.direct = (curve_points, width) if (direct_target(curve_points) and direct_target(width)) else None
+        # (they arrive DETACHED, next to the parameter objects themselves and a fresh `anchor` leaf that keeps the
+        # outputs differentiable: see sample_curves)
+        ctx.direct = direct_params
         ctx.set_materialize_grads(False)
         return xyz, rot, scaling
 
@@ -71,6 +73,9 @@ class _CurveSample(torch.autograd.Function):
         B, n, half_step, wshape = ctx.shape
         dev = cp.device
         direct = ctx.direct is not None and all(direct_grad(p) is not None for p in ctx.direct)
+        if ctx.direct is not None and not direct:
+            raise _lib.CurveGSError("a parameter's FlatGrad(direct=True) gradient buffer was replaced between forward and "
+                                    "backward (call FlatGrad.bind() after an optimizer step that set .grad to None)")
         if direct:
             g_cp, g_w = direct_grad(ctx.direct[0]), direct_grad(ctx.direct[1])
         else:
@@ -85,8 +90,8 @@ class _CurveSample(torch.autograd.Function):
                                          _lib.ptr(g_cp), _lib.ptr(g_w), scratch.data_ptr(), 1 if direct else 0,
                                          _lib.stream(dev)), "cg_sample_bwd")
         if direct:
-            return None, None, None, None
-        return g_cp, g_w.view(wshape), None, None
+            return None, None, None, None, None, None
+        return g_cp, g_w.view(wshape), None, None, None, None
 
 
 def sample_curves(curve_points, width, is_bezier, t):
@@ -94,4 +99,13 @@ def sample_curves(curve_points, width, is_bezier, t):
     if curve_points.shape[0] == 0:
         z = lambda k: curve_points.new_zeros((0, k))
         return z(3), z(4), z(3)
+    if torch.is_grad_enabled() and direct_target(curve_points) and direct_target(width) \
+            and direct_grad(curve_points) is not None and direct_grad(width) is not None:
+        # Direct mode: the op gets the parameters detached, so the autograd graph has no edge to their AccumulateGrad
+        # nodes at all. Those nodes remember the stream they were created on, and every backward that reaches one
+        # makes the calling stream wait for that stream - a cross-stream dependency that invalidates a CUDA-graph
+        # capture taken on any other stream (cudaErrorStreamCaptureIsolation / ...Implicit). A fresh scalar leaf made
+        # on the current stream keeps the outputs differentiable; its gradient is None.
+        anchor = torch.empty((), dtype=torch.float32, device=curve_points.device, requires_grad=True)
+        return _CurveSample.apply(curve_points.detach(), width.detach(), is_bezier, t, anchor, (curve_points, width))
     return _CurveSample.apply(curve_points, width, is_bezier, t)

@@ -8,3 +8,5 @@ for tool in memcheck synccheck; do
 done
 echo "=== racecheck"
 timeout -k 10 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_raster_golden.py -x -q -m gpu 2>&1 | tail -3
+echo "=== memcheck: capacity binning + CUDA-graph capture / replay (round 1: the capture failed under the sanitizer)"
+timeout -k 10 500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_capacity_graph.py -x -q -m gpu 2>&1 | tail -5

@@ -136,9 +136,9 @@ def test_graphed_step_replays_match_eager_steps(cuda_dev):
     gts = [torch.rand(1, H, W, generator=g).to(dev) for _ in cams]
     bg = torch.zeros(3, device=dev)
 
-    def make():
+    def make(direct=False):
         m = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb)
-        return m, FlatGrad([m._curve_points, m._width, m._opacity, m._mask])
+        return m, FlatGrad([m._curve_points, m._width, m._opacity, m._mask], direct=direct)
 
     # eager, exact path
     model, fg = make()
@@ -150,8 +150,10 @@ def test_graphed_step_replays_match_eager_steps(cuda_dev):
         loss.backward()
         eager.append((loss.detach().clone(), fg.flat.clone()))
 
-    # one captured step, replayed per view
-    model2, fg2 = make()
+    # one captured step, replayed per view; the kernels add the curve gradients straight into the flat buffer, so the
+    # captured backward contains no AccumulateGrad node (the node that, bound to the stream of an earlier eager step,
+    # made this capture fail under compute-sanitizer in round 1: profiles/r01_memcheck_capacity.txt)
+    model2, fg2 = make(direct=True)
     scam = StaticCamera(cams[0])
     gt_static = torch.empty_like(gts[0])
 
@@ -249,3 +251,46 @@ def test_overflow_is_sticky_across_replays(cuda_dev):
     torch.cuda.synchronize()
     assert not gs.verify(), "the overflow of the middle replay was lost"
     assert pol.max_seen[(B * n, W, H)] >= Rs[hi]
+
+
+def test_multi_view_step_equals_serial_graph_replays(cuda_dev):
+    """MultiViewStep: V captured copies of the step replayed concurrently. Per view the loss is bit-identical to a
+    single GraphedStep replay of that view; the summed curve gradient equals the serial sum."""
+    from curve_gaussian_b200.graph import MultiViewStep
+    dev = cuda_dev
+    B, n, W, H, V = 200, 12, 256, 192, 4
+    cp, width, opl, isb = synth.random_curves(B, seed=41, line_fraction=0.2)
+    width = width + 0.6
+    cams = [c.to(dev) for c in synth.random_cameras(V, W, H, seed=42)]
+    g = torch.Generator().manual_seed(6)
+    gts = [torch.rand(1, H, W, generator=g).to(dev) for _ in cams]
+    bg = torch.zeros(3, device=dev)
+
+    # serial reference: eager steps, gradients summed in one flat buffer
+    m0 = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb)
+    fg0 = FlatGrad([m0._curve_points, m0._width, m0._opacity, m0._mask])
+    fg0.zero()
+    losses0 = []
+    for cam, gt in zip(cams, gts):
+        m0.prepare_scaling_rot()
+        loss = edge_ssim_loss(render(cam, m0, Pipe(), bg)["render_raw"], gt, clamp=True)
+        loss.backward()
+        losses0.append(loss.detach().clone())
+
+    m1 = GaussianCurveModel(0, n_gaussians=n, device=dev).create_from_curves(cp, width, opl, isb)
+
+    def body(scam, gt):
+        m1.prepare_scaling_rot()
+        loss = edge_ssim_loss(render(scam, m1, Pipe(), bg)["render_raw"], gt, clamp=True)
+        loss.backward()
+        return loss
+
+    mv = MultiViewStep([m1._curve_points, m1._width, m1._opacity, m1._mask], body, cams[0], gts[0], V).capture(cams)
+    for rep in range(2):
+        outs = mv.replay(cams, gts)
+        torch.cuda.synchronize()
+        assert mv.verify()
+        for k in range(V):
+            assert torch.equal(outs[k].detach(), losses0[k]), (rep, k)
+        assert rel(mv.total, fg0.flat) <= 1e-5, rep
+        assert m1._curve_points.grad.data_ptr() == mv.total.data_ptr()
