@@ -470,8 +470,10 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
-  bool done = !inside;
-  float T = 1.0f, C = 0.f, invd_acc = 0.f;
+  // "done" is the sign of T (T itself stays > 0: a pixel stops BEFORE T would drop under 1e-4): one register and
+  // three instructions per walked pair less than a separate flag in a kernel that runs at its 40-register cap
+  float T = inside ? 1.0f : -1.0f, C = 0.f, invd_acc = 0.f;
+#define done (T < 0.f)
   float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3v = 0.f;
   uint32_t last_contributor = 0;
   // candidate list of this warp's 8x4 block (BinKeep::cand / cand_id): tile-relative positions and Gaussian ids of
@@ -527,7 +529,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
             if (!(alpha < 1.0f / 255.0f)) {
               const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
               if (test_T < 0.0001f) {
-                done = true;
+                T = -T;
               } else {
                 C = __fmaf_rn(__fmul_rn(q1.w, alpha), T, C);
                 invd_acc = __fmaf_rn(__fmul_rn(q0.w, alpha), T, invd_acc);
@@ -557,6 +559,8 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");   // (a gather issued for a batch the CTA did not reach)
 
+#undef done
+  T = fabsf(T);
   if (inside) {
     final_T[pix_id] = T;
     n_contrib[pix_id] = last_contributor;
