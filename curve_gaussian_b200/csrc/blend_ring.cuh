@@ -41,6 +41,7 @@ constexpr int RING_UNROLL = CG_RING_UNROLL;   // steps per loop iteration
 #ifndef CG_RING_NB
 #define CG_RING_NB 2
 #endif
+constexpr int RING_LANES = 16;    // lanes (= pixels = elements per epoch) of one ring; two rings per warp
 constexpr int RING_NB = CG_RING_NB;   // blocks that may start within one epoch (each needs a pixel table)
 constexpr int RING_TSLOTS = 3 * RING_NB;
 constexpr uint32_t RING_POS_MASK = 0x07ffffffu;   // list position within the tile; bits 27-30 table slot, bit 31 first-of-block
@@ -56,7 +57,7 @@ struct __align__(16) RingWarp {
   float tT[RING_TSLOTS][32];      // pixel table of a block that starts in an epoch: final_T
   float tD[RING_TSLOTS][32];      //   dL/dpixel
   uint32_t tN[RING_TSLOTS][32];   //   n_contrib
-  float2 torg[RING_TSLOTS];       //   block origin in pixels
+  float2 torg[RING_TSLOTS][2];    //   block origin in pixels
   uint32_t pre[RING_CLASSES + 1]; // blocks in the k largest size classes
 };
 
@@ -95,7 +96,12 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   RingWarp& rw = s_ring[warp];
   const float bg0 = bg[0];
   const bool has_bg = bg0 != 0.f;   // uniform: with a black background its term is an exact zero
-  const int src = int((lane + 31u) & 31u);
+  // the warp runs TWO rings of 16 lanes (one 4x4 half of an 8x4 block each): hl = lane within its ring, hbase = the
+  // ring's first lane. Everything the assignment code calls "uniform" is uniform per ring, and its votes / shuffles
+  // name the ring's lanes only; the step loop itself is executed by both rings in lockstep.
+  const uint32_t hl = lane & 15u, hbase = lane & 16u, ring = lane >> 4;
+  const unsigned hmask = 0xffffu << hbase;
+  const int src = int(hbase | ((hl + 15u) & 15u));
 
   // ---- this warp's blocks: taken one at a time from a global counter, size classes largest first (blend_fwd
   // filed every non-empty block under the half-octave of its candidate count): greedy list scheduling over a
@@ -115,7 +121,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   uint32_t q_bid = 0xffffffffu, q_cnt = 0, q_rx = 0, q_len = 0;
   // (the first four blocks of a warp are fixed - ranks gw, 2 NW - 1 - gw, 2 NW + gw, 4 NW - 1 - gw of the order, so that
   // no warp opens with four of the very largest; everything after that is claimed dynamically)
-  const uint32_t gw = blockIdx.x * RING_WARPS + warp, NW = gridDim.x * RING_WARPS;
+  const uint32_t gw = (blockIdx.x * RING_WARPS + warp) * 2u + ring, NW = gridDim.x * RING_WARPS * 2u;
   auto load_meta = [&](int fixed) {
     const uint32_t at = fixed >= 0 ? uint32_t(fixed) * NW + ((fixed & 1) ? NW - 1u - gw : gw) : 4u * NW + atomicAdd(work, 1u);
     q_bid = 0xffffffffu; q_cnt = 0; q_rx = 0; q_len = 0;
@@ -126,12 +132,12 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
         if (rw.pre[k + step] <= at) k += step;
       q_bid = cls_list[size_t(RING_CLASSES - 1 - k) * nblocks + (at - rw.pre[k])];
       q_cnt = blk_cnt[q_bid];
-      const uint2 r = ranges[q_bid >> 3];
+      const uint2 r = ranges[q_bid >> 4];
       q_rx = r.x;
       q_len = r.y - r.x;
     }
   };
-  if (lane < 4) load_meta(int(lane));
+  if (hl < 4) load_meta(int(hl));
   uint32_t j_next = 0;            // next queue entry to start
   uint32_t cb_rem = 0, cb_base = 0;   // block being consumed: entries left (taken from the end), list base
 
@@ -142,24 +148,24 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     a_addr = 0xffffffffu; a_flag = 0;
 #pragma unroll
     for (int k = 0; k < RING_NB; ++k) nb[k] = 0xffffffffu;
-    uint32_t taken = min(cb_rem, 32u);
-    if (lane < taken) a_addr = cb_base + (cb_rem - 1u - lane);
+    uint32_t taken = min(cb_rem, uint32_t(RING_LANES));
+    if (hl < taken) a_addr = cb_base + (cb_rem - 1u - hl);
     cb_rem -= taken;
     int started = 0;
-    while (taken < 32u && started < RING_NB) {
-      const int qs = int(j_next & 3u);
-      const uint32_t bid = __shfl_sync(FULL, q_bid, qs);
+    while (taken < uint32_t(RING_LANES) && started < RING_NB) {
+      const int qs = int(hbase | (j_next & 3u));
+      const uint32_t bid = __shfl_sync(hmask, q_bid, qs);
       if (bid == 0xffffffffu) break;
       {
-        const uint32_t cnt = __shfl_sync(FULL, q_cnt, qs), rx = __shfl_sync(FULL, q_rx, qs), len = __shfl_sync(FULL, q_len, qs);
+        const uint32_t cnt = __shfl_sync(hmask, q_cnt, qs), rx = __shfl_sync(hmask, q_rx, qs), len = __shfl_sync(hmask, q_len, qs);
         if (int(lane) == qs) load_meta(-1);
         ++j_next;
         if (cnt != 0u) {
-          const uint32_t base = 8u * rx + (bid & 7u) * len;
-          const uint32_t n = min(cnt, 32u - taken);
-          if (lane >= taken && lane < taken + n) {
-            a_addr = base + (cnt - 1u - (lane - taken));
-            if (lane == taken) a_flag = 0x80000000u | (uint32_t((E % 3) * RING_NB + started) << 27);
+          const uint32_t base = 16u * rx + (bid & 15u) * len;
+          const uint32_t n = min(cnt, uint32_t(RING_LANES) - taken);
+          if (hl >= taken && hl < taken + n) {
+            a_addr = base + (cnt - 1u - (hl - taken));
+            if (hl == taken) a_flag = 0x80000000u | (uint32_t((E % 3) * RING_NB + started) << 27);
           }
 #pragma unroll
           for (int k = 0; k < RING_NB; ++k) if (k == started) nb[k] = bid;
@@ -208,7 +214,8 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(-0.5f * s1.y), "f"(s0.x), "f"(s1.z), "f"(0.f) : "memory");
       }
     }
-    if (m >= 1 ? real_m1 == 0u : (m == 0 && real_0 == 0u)) break;   // nothing in flight and nothing left
+    // nothing in flight and nothing left, in either ring (a ring that runs dry first idles through empty epochs)
+    if (__all_sync(FULL, m >= 1 ? real_m1 == 0u : (m == 0 && real_0 == 0u))) break;
     {
       // records + Gaussian ids of epoch E = m+1, pixel tables of the blocks that start in it
       const int E = m + 1;
@@ -230,10 +237,10 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
           const uint32_t nb = nbA[k];
           if (nb != 0xffffffffu) {
             const int ts = (E % 3) * RING_NB + k;
-            const uint32_t tile = nb >> 3, b = nb & 7u;
-            const uint32_t bx0 = (tile % uint32_t(grid_x)) * TILE_X + (b & 1u) * 8u;
+            const uint32_t tile = nb >> 4, b = (nb >> 1) & 7u;
+            const uint32_t bx0 = (tile % uint32_t(grid_x)) * TILE_X + (b & 1u) * 8u + (nb & 1u) * 4u;
             const uint32_t by0 = (tile / uint32_t(grid_x)) * TILE_Y + (b >> 1) * 4u;
-            const uint32_t px = bx0 + (lane & 7u), py = by0 + (lane >> 3);
+            const uint32_t px = bx0 + (hl & 3u), py = by0 + (hl >> 2);
             if (px < uint32_t(W) && py < uint32_t(H)) {
               const size_t pid = size_t(W) * py + px;
               cp_async4(&rw.tT[ts][lane], final_T + pid);
@@ -242,7 +249,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
             } else {
               rw.tT[ts][lane] = 0.f; rw.tD[ts][lane] = 0.f; rw.tN[ts][lane] = 0u;
             }
-            if (lane == 0) rw.torg[ts] = make_float2(float(bx0), float(by0));
+            if (hl == 0) rw.torg[ts][ring] = make_float2(float(bx0), float(by0));
           }
         }
       }
@@ -263,7 +270,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     const uint32_t stA_addr = smem_u32(&rw.eA[m & 1][lane]), stB_addr = smem_u32(&rw.eB[m & 1][lane]);
     const uint32_t snap_addr = smem_u32(&rw.snap[lane][0]);
 #pragma unroll RING_UNROLL
-    for (uint32_t u = 0; u < 32u; ++u) {
+    for (uint32_t u = 0; u < uint32_t(RING_LANES); ++u) {
       T = __shfl_sync(FULL, T, src);
       Rp = __shfl_sync(FULL, Rp, src);
       dLp = __shfl_sync(FULL, dLp, src);
@@ -288,21 +295,21 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
             "@sw mov.f32 %14, 0f00000000;\n\t}"
             : "+f"(ex), "+f"(ey), "+f"(eo), "+f"(col), "+f"(ca), "+f"(cb), "+f"(cc), "+f"(poswf),
               "+f"(S0), "+f"(S1), "+f"(S2), "+f"(S3), "+f"(S4), "+f"(S5), "+f"(S7), "+f"(spad)
-            : "r"(lane), "r"(u), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr)
+            : "r"(hl), "r"(u), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr)
             : "memory");
       }
       const uint32_t posw = __float_as_uint(poswf);
       if (posw & 0x80000000u) {
         // first element of its block (back to front): the arriving slot becomes pixel p of that block
-        const uint32_t ts = (posw >> 27) & 15u, p = (u - lane) & 31u;
-        T = rw.tT[ts][p];
+        const uint32_t ts = (posw >> 27) & 15u, p = (u - hl) & 15u, tp = hbase | p;
+        T = rw.tT[ts][tp];
         Tf = T;
-        dLp = rw.tD[ts][p];
-        nc = int(rw.tN[ts][p]);
+        dLp = rw.tD[ts][tp];
+        nc = int(rw.tN[ts][tp]);
         Rp = 0.f;
-        const float2 org = rw.torg[ts];
-        pxf = org.x + float(p & 7u);
-        pyf = org.y + float(p >> 3);
+        const float2 org = rw.torg[ts][ring];
+        pxf = org.x + float(p & 3u);
+        pyf = org.y + float(p >> 2);
       }
       bool contrib = int(posw & RING_POS_MASK) < nc;
       const float dx = __fsub_rn(ex, pxf), dy = __fsub_rn(ey, pyf);

@@ -225,12 +225,13 @@ struct ImgState {
   uint32_t* tile_maxc;  // per blend CTA (tile * BLEND_SUBS + sub): max n_contrib over its pixels (backward start)
   uint32_t* tile_order; // blend CTA ids, longest list first: the launch order of the blend CTAs (forward, and the
                         // lane-per-pixel backward)
-  // 8x4 pixel blocks (8 per tile, block id = tile * 8 + warp), written by blend_fwd for the ring backward:
-  uint32_t* blk_cnt;    // entries of the block's candidate list (BinKeep::cand) that lie below the block's last contributor
+  // 4x4 pixel blocks (16 per tile, block id = tile * 16 + warp * 2 + half: the left / right half of a forward warp's
+  // 8x4 block), written by blend_fwd for the ring backward:
+  uint32_t* blk_cnt;    // entries of the block's contributor list (BinKeep::cand)
   uint32_t* cls_count;  // [RING_CLASSES] non-empty blocks per size class (class = half-octave of blk_cnt), then
                         // [RING_CLASSES], [RING_CLASSES + 1] = work / exit counters of blend_bwd_ring (left at zero by it);
                         // zero-filled together with `ranges` at the start of every forward
-  uint32_t* cls_list;   // [RING_CLASSES][tiles * 8] block ids per class, in arrival order
+  uint32_t* cls_list;   // [RING_CLASSES][tiles * 16] block ids per class, in arrival order
   static ImgState carve(void* base, int W, int H, size_t* bytes) {
     Carver c(base);
     ImgState s;
@@ -242,8 +243,8 @@ struct ImgState {
     s.cls_count = c.take<uint32_t>(RING_CLASSES + 32);   // directly behind ranges: one memset clears both
     s.tile_maxc = c.take<uint32_t>(tiles * BLEND_SUBS);
     s.tile_order = c.take<uint32_t>(tiles * BLEND_SUBS);
-    s.blk_cnt = c.take<uint32_t>(tiles * 8);
-    s.cls_list = c.take<uint32_t>(size_t(RING_CLASSES) * tiles * 8);
+    s.blk_cnt = c.take<uint32_t>(tiles * 16);
+    s.cls_list = c.take<uint32_t>(size_t(RING_CLASSES) * tiles * 16);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return s;
   }
@@ -251,18 +252,19 @@ struct ImgState {
 
 struct BinKeep {
   uint32_t* point_list;   // Gaussian index per sorted tile-instance (the reference's point_list)
-  // Candidate lists of the 8x4 pixel blocks: block b (0..7) of a tile whose range is [x, y) owns
-  // cand[8 * x + b * (y - x) ...]: the tile-relative list positions, ascending, of the instances that passed the
-  // forward's block_candidate test for that block, and cand_id[...] their Gaussian indices (written by blend_fwd,
-  // consumed back to front by blend_bwd_ring).
+  // Contributor lists of the 4x4 pixel blocks: block b (0..15) of a tile whose range is [x, y) owns
+  // cand[16 * x + b * (y - x) ...]: the tile-relative list positions, ascending, of the instances that the forward
+  // blended into at least one pixel of the block, and cand_id[...] their Gaussian indices (written by blend_fwd,
+  // consumed back to front by blend_bwd_ring). 128 bytes of address space per instance, of which the forward writes
+  // about 13 (1.6 entries per instance-and-8x4-block pair that contributes).
   uint32_t* cand;
   uint32_t* cand_id;
   static BinKeep carve(void* base, int64_t R, size_t* bytes) {
     Carver c(base);
     BinKeep b;
     b.point_list = c.take<uint32_t>(R + 1);
-    b.cand = c.take<uint32_t>(8 * size_t(R + 1));
-    b.cand_id = c.take<uint32_t>(8 * size_t(R + 1));
+    b.cand = c.take<uint32_t>(16 * size_t(R + 1));
+    b.cand_id = c.take<uint32_t>(16 * size_t(R + 1));
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }

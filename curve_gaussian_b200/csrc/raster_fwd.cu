@@ -407,10 +407,15 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const uint32_t blk_x = tile_x * TILE_X + (warp & 1) * 8;
   const uint32_t blk_y = tile_y * TILE_Y + sub * BLEND_ROWS + (warp >> 1) * 4;
-  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
-  const bool inside = pix_x < uint32_t(W) && pix_y < uint32_t(H);
-  const uint32_t pix_id = uint32_t(W) * pix_y + pix_x;
-  const float pxf = float(pix_x), pyf = float(pix_y);
+  // the pixel is kept as two floats only (the integer coordinates are recovered at the end): at the kernel's
+  // 40-register cap the compiler otherwise keeps the integers and converts them again for every walked pair
+  float pxf, pyf, T;
+  {
+    const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
+    T = pix_x < uint32_t(W) && pix_y < uint32_t(H) ? 1.0f : -1.0f;   // (see `done` below)
+    pxf = float(pix_x); pyf = float(pix_y);
+    asm volatile("" : "+f"(pxf), "+f"(pyf));
+  }
   // pixel block of this warp, clipped to the image
   const float bx0 = float(blk_x), bx1 = float(min(blk_x + 7u, uint32_t(W) - 1u));
   const float by0 = float(blk_y), by1 = float(min(blk_y + 3u, uint32_t(H) - 1u));
@@ -472,16 +477,16 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
 
   // "done" is the sign of T (T itself stays > 0: a pixel stops BEFORE T would drop under 1e-4): one register and
   // three instructions per walked pair less than a separate flag in a kernel that runs at its 40-register cap
-  float T = inside ? 1.0f : -1.0f, C = 0.f, invd_acc = 0.f;
+  float C = 0.f, invd_acc = 0.f;
 #define done (T < 0.f)
   float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3v = 0.f;
   uint32_t last_contributor = 0;
-  // candidate list of this warp's 8x4 block (BinKeep::cand / cand_id): tile-relative positions and Gaussian ids of
-  // the instances that pass the block test, in list order; cand_eff = how many of them lie at or below the block's
-  // last contributor
+  // contributor lists of the two 4x4 halves of this warp's 8x4 block (BinKeep::cand / cand_id): tile-relative
+  // positions and Gaussian ids of the instances blended into at least one pixel of the half, in list order
   // (32-bit offsets into the lists: the kernel runs at 40 registers)
-  const uint32_t cand_start = 8u * range.x + (sub * BLEND_WARPS + warp) * uint32_t(total);
-  uint32_t cand_off = cand_start, cand_eff = cand_start;
+  const uint32_t cand_start = 16u * range.x + (sub * BLEND_WARPS + warp) * 2u * uint32_t(total);
+  uint32_t cand_l = cand_start, cand_r = cand_start + uint32_t(total);
+  const bool left = (lane & 4u) == 0u;
 
   int todo = total;
   for (int b = 0; b < rounds; ++b, todo -= BATCH) {
@@ -509,16 +514,12 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
         cand = block_candidate(q1.x, q1.y, q0.x, q0.y, q0.z, q1.z, bx0, bx1, by0, by1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, cand);
-      if (cand) {
-        uint32_t below;   // candidates in lower lanes (shl clamps: lane 0 shifts everything out)
-        asm("shl.b32 %0, %1, %2;" : "=r"(below) : "r"(mask), "r"(32u - lane));
-        const uint32_t at = cand_off + __popc(below);
-        cand_lists[at] = pos0 + uint32_t(idx);
-        cand_ids[at] = ids[idx];
-      }
+      uint32_t mine = 0;   // bit k: this pixel blended the chunk's record k
       while (mask) {
-        const int j = r + __ffs(int(mask)) - 1;
-        mask &= mask - 1;
+        const uint32_t rest = mask & (mask - 1);
+        const uint32_t bit = mask ^ rest;          // lowest candidate
+        const int j = r + (31 - __clz(int(bit)));
+        mask = rest;
         if (!done) {
           const float4 q0 = *reinterpret_cast<const float4*>(&batch[j].ca);   // ca cb cc invd
           const float4 q1 = *reinterpret_cast<const float4*>(&batch[j].x);    // x y o col
@@ -541,26 +542,31 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
                   M3v = __fmaf_rn(__fmul_rn(mp.w, alpha), T, M3v);
                 }
                 T = test_T;
-                last_contributor = pos0 + uint32_t(j) + 1u;
+                mine |= bit;
               }
             }
           }
         }
       }
-      const uint32_t mask0 = __ballot_sync(0xffffffffu, cand);   // again: the walk consumed `mask`, and a register is dearer than a vote
-      if (mask0) {
-        // the block's last contributor so far lies in this chunk <=> it is newer than the chunk's first position
-        const uint32_t mc_now = __reduce_max_sync(0xffffffffu, last_contributor);
-        const uint32_t first = pos0 + uint32_t(r);
-        if (mc_now > first) cand_eff = cand_off + __popc(mask0 & (0xffffffffu >> (31u - (mc_now - 1u - first))));
-        cand_off += __popc(mask0);
+      if (mine) last_contributor = pos0 + uint32_t(r) + 32u - uint32_t(__clz(int(mine)));   // (1-based position of the last blended)
+      // records some pixel of the left / right half blended: lane k files record k of the chunk
+      const uint32_t hit_l = __reduce_or_sync(0xffffffffu, left ? mine : 0u);
+      const uint32_t hit_r = __reduce_or_sync(0xffffffffu, left ? 0u : mine);
+      if ((hit_l | hit_r) >> lane & 1u) {
+        const uint32_t lt = (1u << lane) - 1u, pos = pos0 + uint32_t(idx), id = ids[idx];
+        if (hit_l >> lane & 1u) { const uint32_t at = cand_l + __popc(hit_l & lt); cand_lists[at] = pos; cand_ids[at] = id; }
+        if (hit_r >> lane & 1u) { const uint32_t at = cand_r + __popc(hit_r & lt); cand_lists[at] = pos; cand_ids[at] = id; }
       }
+      cand_l += __popc(hit_l);
+      cand_r += __popc(hit_r);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");   // (a gather issued for a batch the CTA did not reach)
 
 #undef done
   T = fabsf(T);
+  const uint32_t pix_x = uint32_t(pxf), pix_y = uint32_t(pyf), pix_id = uint32_t(W) * pix_y + pix_x;
+  const bool inside = pix_x < uint32_t(W) && pix_y < uint32_t(H);
   if (inside) {
     final_T[pix_id] = T;
     n_contrib[pix_id] = last_contributor;
@@ -576,11 +582,12 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
   }
   uint32_t mc = inside ? last_contributor : 0u;
   mc = __reduce_max_sync(0xffffffffu, mc);
-  if (lane == 0) {
-    atomicMax(&s_maxc, mc);
-    // the block joins the list of its size class (half octaves of the candidate count): the ring backward takes the
-    // classes largest first, which is all the ordering its greedy scheduling needs
-    const uint32_t n = cand_eff - cand_start, bid = tile * 8 + sub * BLEND_WARPS + warp;
+  if (lane == 0) atomicMax(&s_maxc, mc);
+  if (lane < 2) {
+    // each half joins the list of its size class (half octaves of the contributor count): the ring backward takes
+    // the classes largest first, which is all the ordering its greedy scheduling needs
+    const uint32_t n = lane ? cand_r - cand_start - uint32_t(total) : cand_l - cand_start;
+    const uint32_t bid = (tile * 8 + sub * BLEND_WARPS + warp) * 2u + lane;
     blk_cnt[bid] = n;
     if (n) {
       const uint32_t msb = 31u - uint32_t(__clz(int(n)));
@@ -708,11 +715,11 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
   if (s->render_geo)
     launch_k(blend_fwd<true>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, g.grec, bk.point_list, W, H, s->bg,
              out_color, out_invd, out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, bk.cand_id, im.blk_cnt,
-             im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
+             im.cls_count, im.cls_list, uint32_t(tiles) * 16u);
   else
     launch_k(blend_fwd<false>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, g.grec, bk.point_list, W, H, s->bg,
              out_color, out_invd, out_map, im.final_T, im.n_contrib, im.tile_maxc, bk.cand, bk.cand_id, im.blk_cnt,
-             im.cls_count, im.cls_list, uint32_t(tiles) * 8u);
+             im.cls_count, im.cls_list, uint32_t(tiles) * 16u);
   CG_LAUNCH_CHECK(s->debug, st);
   return CG_OK;
 }
