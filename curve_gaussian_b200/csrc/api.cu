@@ -268,6 +268,9 @@ int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
       return CG_OK;
     case 7: src = im.n_contrib; bytes = size_t(W) * H * 4; break;
     case 8: src = im.final_T; bytes = size_t(W) * H * 4; break;
+    case 9: src = im.blk_cnt; bytes = tiles * 16 * 4; break;
+    case 10: CG_ARG(bin_keep != nullptr, "bin_keep"); src = bk.cand; bytes = size_t(R) * 16 * 4; break;
+    case 11: CG_ARG(bin_keep != nullptr, "bin_keep"); src = bk.cand_id; bytes = size_t(R) * 16 * 4; break;
     default: set_error("debug_fetch: unknown selector %d", which); return CG_ERR_ARG;
   }
   CG_ARG(src != nullptr, "state buffer");

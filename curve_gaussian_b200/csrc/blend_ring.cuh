@@ -54,10 +54,9 @@ struct __align__(16) RingWarp {
   float4 eB[2][32];               //                              conic a, b, c, position|flags
   float4 snap[32][3];             // sums of the element a lane just finished: S0..S3 | S4 S5 S7 - | conic a b c -
   uint32_t gid[4][32];            // Gaussian index of the elements of an epoch (for the flush, two epochs later)
-  float tT[RING_TSLOTS][32];      // pixel table of a block that starts in an epoch: final_T
-  float tD[RING_TSLOTS][32];      //   dL/dpixel
-  uint32_t tN[RING_TSLOTS][32];   //   n_contrib
-  float2 torg[RING_TSLOTS][2];    //   block origin in pixels
+  float4 tQ[RING_TSLOTS][32];     // pixel table of a block that starts in an epoch: final_T, dL/dpixel, n_contrib, x
+  float tY[RING_TSLOTS][32];      //   y
+  float4 zero;                    // (0, 0, 0, 0): what the switch reloads the sums from
   uint32_t pre[RING_CLASSES + 1]; // blocks in the k largest size classes
 };
 
@@ -113,7 +112,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(FULL, inc, o); if (int(lane) >= o) inc += n; }
     rw.pre[lane + 1] = inc;
-    if (lane == 0) rw.pre[0] = 0;
+    if (lane == 0) { rw.pre[0] = 0; rw.zero = make_float4(0.f, 0.f, 0.f, 0.f); }
     __syncwarp();
   }
   const uint32_t n_items = rw.pre[RING_CLASSES];
@@ -241,15 +240,17 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
             const uint32_t bx0 = (tile % uint32_t(grid_x)) * TILE_X + (b & 1u) * 8u + (nb & 1u) * 4u;
             const uint32_t by0 = (tile / uint32_t(grid_x)) * TILE_Y + (b >> 1) * 4u;
             const uint32_t px = bx0 + (hl & 3u), py = by0 + (hl >> 2);
+            float* q = reinterpret_cast<float*>(&rw.tQ[ts][lane]);
             if (px < uint32_t(W) && py < uint32_t(H)) {
               const size_t pid = size_t(W) * py + px;
-              cp_async4(&rw.tT[ts][lane], final_T + pid);
-              cp_async4(&rw.tD[ts][lane], dL_dpix + pid);
-              cp_async4(&rw.tN[ts][lane], n_contrib + pid);
+              cp_async4(q, final_T + pid);
+              cp_async4(q + 1, dL_dpix + pid);
+              cp_async4(q + 2, n_contrib + pid);
             } else {
-              rw.tT[ts][lane] = 0.f; rw.tD[ts][lane] = 0.f; rw.tN[ts][lane] = 0u;
+              q[0] = 0.f; q[1] = 0.f; q[2] = 0.f;
             }
-            if (hl == 0) rw.torg[ts][ring] = make_float2(float(bx0), float(by0));
+            q[3] = float(px);
+            rw.tY[ts][lane] = float(py);
           }
         }
       }
@@ -269,6 +270,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     // ================= the 32 steps of period m =================
     const uint32_t stA_addr = smem_u32(&rw.eA[m & 1][lane]), stB_addr = smem_u32(&rw.eB[m & 1][lane]);
     const uint32_t snap_addr = smem_u32(&rw.snap[lane][0]);
+    const uint32_t zero_addr = smem_u32(&rw.zero);
 #pragma unroll RING_UNROLL
     for (uint32_t u = 0; u < uint32_t(RING_LANES); ++u) {
       T = __shfl_sync(FULL, T, src);
@@ -290,26 +292,25 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
             "@sw st.shared.v4.f32 [%18+32], {%4, %5, %6, %7};\n\t"
             "@sw ld.shared.v4.f32 {%0, %1, %2, %3}, [%19];\n\t"
             "@sw ld.shared.v4.f32 {%4, %5, %6, %7}, [%20];\n\t"
-            "@sw mov.f32 %8, 0f00000000;\n\t@sw mov.f32 %9, 0f00000000;\n\t@sw mov.f32 %10, 0f00000000;\n\t"
-            "@sw mov.f32 %11, 0f00000000;\n\t@sw mov.f32 %12, 0f00000000;\n\t@sw mov.f32 %13, 0f00000000;\n\t"
-            "@sw mov.f32 %14, 0f00000000;\n\t}"
+            "@sw ld.shared.v4.f32 {%8, %9, %10, %11}, [%21];\n\t"      // (zeros: two loads instead of seven moves)
+            "@sw ld.shared.v4.f32 {%12, %13, %14, %15}, [%21];\n\t}"
             : "+f"(ex), "+f"(ey), "+f"(eo), "+f"(col), "+f"(ca), "+f"(cb), "+f"(cc), "+f"(poswf),
               "+f"(S0), "+f"(S1), "+f"(S2), "+f"(S3), "+f"(S4), "+f"(S5), "+f"(S7), "+f"(spad)
-            : "r"(hl), "r"(u), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr)
+            : "r"(hl), "r"(u), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr), "r"(zero_addr)
             : "memory");
       }
       const uint32_t posw = __float_as_uint(poswf);
       if (posw & 0x80000000u) {
         // first element of its block (back to front): the arriving slot becomes pixel p of that block
         const uint32_t ts = (posw >> 27) & 15u, p = (u - hl) & 15u, tp = hbase | p;
-        T = rw.tT[ts][tp];
+        const float4 q = rw.tQ[ts][tp];
+        T = q.x;
         Tf = T;
-        dLp = rw.tD[ts][tp];
-        nc = int(rw.tN[ts][tp]);
+        dLp = q.y;
+        nc = __float_as_int(q.z);
         Rp = 0.f;
-        const float2 org = rw.torg[ts][ring];
-        pxf = org.x + float(p & 3u);
-        pyf = org.y + float(p >> 2);
+        pxf = q.w;
+        pyf = rw.tY[ts][tp];
       }
       bool contrib = int(posw & RING_POS_MASK) < nc;
       const float dx = __fsub_rn(ex, pxf), dy = __fsub_rn(ey, pyf);

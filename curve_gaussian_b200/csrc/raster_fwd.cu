@@ -520,33 +520,29 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
         const uint32_t bit = mask ^ rest;          // lowest candidate
         const int j = r + (31 - __clz(int(bit)));
         mask = rest;
-        if (!done) {
-          const float4 q0 = *reinterpret_cast<const float4*>(&batch[j].ca);   // ca cb cc invd
-          const float4 q1 = *reinterpret_cast<const float4*>(&batch[j].x);    // x y o col
-          const float dx = __fsub_rn(q1.x, pxf), dy = __fsub_rn(q1.y, pyf);
-          const float power = gauss_power(q0.x, q0.y, q0.z, dx, dy);
-          if (!(power > 0.0f)) {
-            const float alpha = fminf(0.99f, __fmul_rn(q1.z, expf(power)));
-            if (!(alpha < 1.0f / 255.0f)) {
-              const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
-              if (test_T < 0.0001f) {
-                T = -T;
-              } else {
-                C = __fmaf_rn(__fmul_rn(q1.w, alpha), T, C);
-                invd_acc = __fmaf_rn(__fmul_rn(q0.w, alpha), T, invd_acc);
-                if (GEO) {
-                  const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
-                  M0 = __fmaf_rn(__fmul_rn(mp.x, alpha), T, M0);
-                  M1 = __fmaf_rn(__fmul_rn(mp.y, alpha), T, M1);
-                  M2 = __fmaf_rn(__fmul_rn(mp.z, alpha), T, M2);
-                  M3v = __fmaf_rn(__fmul_rn(mp.w, alpha), T, M3v);
-                }
-                T = test_T;
-                mine |= bit;
-              }
-            }
+        // straight-line form: every lane evaluates the pair and the updates are predicated (five issue slots per pair
+        // fewer than skipping with branches, which only pays when all 32 pixels fail the same test)
+        const float4 q0 = *reinterpret_cast<const float4*>(&batch[j].ca);   // ca cb cc invd
+        const float4 q1 = *reinterpret_cast<const float4*>(&batch[j].x);    // x y o col
+        const float dx = __fsub_rn(q1.x, pxf), dy = __fsub_rn(q1.y, pyf);
+        const float power = gauss_power(q0.x, q0.y, q0.z, dx, dy);
+        const float alpha = fminf(0.99f, __fmul_rn(q1.z, expf(power)));
+        const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+        const bool act = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+        const bool stop = test_T < 0.0001f;
+        if (act && !stop) {
+          C = __fmaf_rn(__fmul_rn(q1.w, alpha), T, C);
+          invd_acc = __fmaf_rn(__fmul_rn(q0.w, alpha), T, invd_acc);
+          if (GEO) {
+            const float4 mp = *reinterpret_cast<const float4*>(&batch[j].m0);
+            M0 = __fmaf_rn(__fmul_rn(mp.x, alpha), T, M0);
+            M1 = __fmaf_rn(__fmul_rn(mp.y, alpha), T, M1);
+            M2 = __fmaf_rn(__fmul_rn(mp.z, alpha), T, M2);
+            M3v = __fmaf_rn(__fmul_rn(mp.w, alpha), T, M3v);
           }
+          mine |= bit;
         }
+        if (act) T = stop ? -T : test_T;
       }
       if (mine) last_contributor = pos0 + uint32_t(r) + 32u - uint32_t(__clz(int(mine)));   // (1-based position of the last blended)
       // records some pixel of the left / right half blended: lane k files record k of the chunk

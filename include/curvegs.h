@@ -170,6 +170,9 @@ int cg_mark_visible(int64_t P, const float* means3D, const float* viewmatrix,
  *        2 = tile ranges (uint32 pairs, tiles)  3 = tiles_touched (uint32, P)
  *        4 = means2D (float2, P)  5 = depths (float, P)  6 = conic_opacity (float4, P)
  *        7 = n_contrib (uint32, W*H)  8 = final_T (float, W*H)
+ *        9 = contributor count of every 4x4 pixel block (uint32, tiles*16; block = tile*16 + 8x4 block*2 + half)
+ *        10 / 11 = contributor lists of the 4x4 blocks: tile-relative list positions / Gaussian indices
+ *                  (uint32, 16*R; block b of a tile with range [x, y) starts at 16*x + b*(y-x))
  * Keys (0) are only valid between cg_raster_fwd_blend and the next call that
  * reuses bin_scratch. dst is a DEVICE pointer with room for the array. */
 int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
