@@ -80,7 +80,7 @@ int launch_bwd(const cg_raster_settings* s, int64_t P, int64_t R, const float* m
                float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
                float* dL_drotations, float* dL_dall_map_in, cudaStream_t st);
 int launch_mark_visible(int64_t P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t st);
-int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, const void* bin_keep,
+int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, const void* img, const void* bin_keep,
                         const void* bin_scratch, uint64_t* dst, cudaStream_t st);
 
 static int check_settings(const cg_raster_settings* s) {
@@ -254,7 +254,7 @@ int cg_raster_debug_fetch(int which, int64_t P, int64_t R, int32_t W, int32_t H,
     case 0:
       // the reference's 64-bit keys are not materialised (see BinScratch); rebuild them from the sorted state
       CG_ARG(bin_scratch != nullptr && bin_keep != nullptr && geom != nullptr, "bin_scratch/bin_keep/geom");
-      return launch_rebuild_keys(P, R, W, H, geom, bin_keep, bin_scratch, reinterpret_cast<uint64_t*>(dst), st);
+      return launch_rebuild_keys(P, R, W, H, geom, img, bin_keep, bin_scratch, reinterpret_cast<uint64_t*>(dst), st);
     case 1: CG_ARG(bin_keep != nullptr, "bin_keep"); src = bk.point_list; bytes = size_t(R) * 4; break;
     case 2: src = im.ranges; bytes = tiles * 8; break;
     case 3: src = g.tiles; bytes = size_t(P) * 4; break;

@@ -192,6 +192,13 @@ struct SortBufs {
   }
 };
 
+// Super-tile binning geometry (binning.cuh).
+constexpr int ST_SHIFT = 3;                    // super-tile = 8 x 8 tiles
+constexpr int ST_SIDE = 1 << ST_SHIFT;
+constexpr int BIN_EPL = 4;                     // copies per lane
+constexpr int BIN_CHUNK = 32 * BIN_EPL;        // copies per chunk (one warp)
+constexpr int BIN_MAX_SUPERTILES = 16384;      // (a 16384 x 16384 pixel image); larger images use the sort path
+
 struct GeomState {
   Rec* grec;         // per Gaussian: conic, 1/depth, mean2D, opacity, colour, all_map (valid where tiles > 0)
   float* depth;
@@ -199,7 +206,7 @@ struct GeomState {
   uint2* rect;       // packed tile rect: x = min.x | min.y<<16, y = max.x | max.y<<16
   uint32_t* blk_sum;
   uint32_t* blk_prefix;
-  uint32_t* total;   // [0] = R
+  uint32_t* total;   // [0] = R; [1] = number of (super-tile, Gaussian) copies (super-tile binning)
   SortBufs<uint32_t> gs;   // the P Gaussians sorted by depth bits (value = Gaussian index), see BinScratch
   static GeomState carve(void* base, int64_t P, size_t* bytes) {
     Carver c(base);
@@ -232,6 +239,10 @@ struct ImgState {
                         // [RING_CLASSES], [RING_CLASSES + 1] = work / exit counters of blend_bwd_ring (left at zero by it);
                         // zero-filled together with `ranges` at the start of every forward
   uint32_t* cls_list;   // [RING_CLASSES][tiles * 16] block ids per class, in arrival order
+  // super-tile binning (binning.cuh); tile_cnt and st_ranges are zero-filled with `ranges`
+  uint32_t* tile_cnt;    // [tiles] instances per tile
+  uint2* st_ranges;      // [super-tiles] span of each super-tile in the sorted copy list
+  uint32_t* chunk_start; // [super-tiles + 1] first chunk of each super-tile
   static ImgState carve(void* base, int W, int H, size_t* bytes) {
     Carver c(base);
     ImgState s;
@@ -240,7 +251,11 @@ struct ImgState {
     s.final_T = c.take<float>(npix);
     s.n_contrib = c.take<uint32_t>(npix);
     s.ranges = c.take<uint2>(tiles);
-    s.cls_count = c.take<uint32_t>(RING_CLASSES + 32);   // directly behind ranges: one memset clears both
+    s.cls_count = c.take<uint32_t>(RING_CLASSES + 32);   // directly behind ranges: one memset clears all four
+    const size_t nst = size_t((W + TILE_X * ST_SIDE - 1) / (TILE_X * ST_SIDE)) * ((H + TILE_Y * ST_SIDE - 1) / (TILE_Y * ST_SIDE));
+    s.tile_cnt = c.take<uint32_t>(tiles);
+    s.st_ranges = c.take<uint2>(nst);
+    s.chunk_start = c.take<uint32_t>(nst + 1);
     s.tile_maxc = c.take<uint32_t>(tiles * BLEND_SUBS);
     s.tile_order = c.take<uint32_t>(tiles * BLEND_SUBS);
     s.blk_cnt = c.take<uint32_t>(tiles * 16);
@@ -281,11 +296,17 @@ struct BinKeep {
 // but the big R-sized passes shrink from 6 x 24 B to 2 x 16 B per instance.
 struct BinScratch {
   SortBufs<uint32_t> is;
+  // super-tile binning (binning.cuh): per chunk of BIN_CHUNK copies and tile of its super-tile
+  uint16_t* ccnt;    // [chunks][64] copies of the chunk covering the tile
+  uint32_t* cbase;   // [chunks][64] the same, summed over the super-tile's earlier chunks
+  static size_t max_chunks(int64_t R) { return size_t(R > 0 ? R : 0) / BIN_CHUNK + BIN_MAX_SUPERTILES + 1; }
   static BinScratch carve(void* base, int64_t P, int64_t R, size_t* bytes) {
     (void)P;
     Carver c(base);
     BinScratch b;
     b.is = SortBufs<uint32_t>::carve(c, R);
+    b.ccnt = c.take<uint16_t>(max_chunks(R) * 64);
+    b.cbase = c.take<uint32_t>(max_chunks(R) * 64);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;
   }

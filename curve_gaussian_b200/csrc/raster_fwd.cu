@@ -8,9 +8,11 @@
 //   key emission rasterizer_impl.cu:70-111
 //   ranges       rasterizer_impl.cu:116-138
 //   blend        forward.cu:279-417
+#include <cstring>
 #include "common.cuh"
 #include "math.cuh"
 #include "stage.cuh"
+#include "binning.cuh"
 
 namespace cg {
 
@@ -119,7 +121,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
 }
 
 // Single CTA: exclusive scan of the per-block sums, total -> g.total[0].
-__global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState g) {
+__global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState g, int slot) {
   pdl_wait();
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
     if (threadIdx.x == 1023) s_carry = carry + s_w[w] + inc;
     __syncthreads();
   }
-  if (threadIdx.x == 0) g.total[0] = s_carry;
+  if (threadIdx.x == 0) g.total[slot] = s_carry;
 }
 
 // Per-Gaussian sort input: key = bits of the view-space depth (culled Gaussians emit nothing,
@@ -165,13 +167,19 @@ init_depth_keys(int64_t P, GeomState g, uint32_t* __restrict__ keys, uint32_t* _
   vals[i] = uint32_t(i);
 }
 
-// Block sums of tiles_touched taken in depth order (perm = Gaussian indices sorted by depth).
+// Block sums of tiles_touched (shift = 0) or of the number of super-tiles overlapped (shift = ST_SHIFT), taken in
+// depth order (perm = Gaussian indices sorted by depth).
 __global__ void __launch_bounds__(256)
-perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
+perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int shift) {
   pdl_wait();
   __shared__ uint32_t s_wsum[8];
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  uint32_t v = (i < P) ? g.tiles[perm[i]] : 0u;
+  uint32_t v = 0;
+  if (i < P) {
+    const uint32_t idx = perm[i];
+    v = g.tiles[idx];
+    if (shift && v) v = rect_area(st_rect(g.rect[idx], shift));   // super-tiles overlapped instead of tiles
+  }
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) s_wsum[threadIdx.x >> 5] = v;
   __syncthreads();
@@ -191,7 +199,8 @@ perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g) {
 // work is balanced no matter how uneven the rects are.
 __global__ void __launch_bounds__(256)
 emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x, uint32_t* __restrict__ keys,
-          uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ nr_out, uint32_t* __restrict__ hist, int bpp) {
+          uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ nr_out, uint32_t* __restrict__ hist, int bpp,
+          int shift) {
   pdl_wait();
   // digit histograms of the tile sort that follows (two passes of bpp bits, see radix_sort_begin): counted here,
   // while the keys are in registers anyway, instead of in a pass of their own over the R keys
@@ -213,7 +222,12 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t idx = (i < P) ? perm[i] : 0u;
-  const uint32_t cnt = (i < P) ? g.tiles[idx] : 0u;
+  uint32_t cnt = (i < P) ? g.tiles[idx] : 0u;
+  uint2 my_rect = make_uint2(0u, 0u);
+  if (cnt) {
+    my_rect = g.rect[idx];
+    if (shift) { my_rect = st_rect(my_rect, shift); cnt = rect_area(my_rect); }   // (grid_x is then in super-tiles)
+  }
   uint32_t inc = cnt;
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
@@ -221,7 +235,7 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
   }
   if (lane == 31) s_w[w] = inc;
   s_idx[threadIdx.x] = idx;
-  if (cnt) s_rect[threadIdx.x] = g.rect[idx];
+  if (cnt) s_rect[threadIdx.x] = my_rect;
   __syncthreads();
   uint32_t wb = 0;
   for (uint32_t k = 0; k < w; ++k) wb += s_w[k];
@@ -256,16 +270,6 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
     if (s_hist[0][threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[0][threadIdx.x]);
     if (s_hist[1][threadIdx.x]) atomicAdd(&hist[256 + threadIdx.x], s_hist[1][threadIdx.x]);
   }
-}
-
-// The reference's 64-bit sort keys, rebuilt for parity checks: tile<<32 | float_bits(depth).
-__global__ void __launch_bounds__(256)
-rebuild_keys(int64_t R, const uint32_t* __restrict__ tiles_sorted, const uint32_t* __restrict__ point_list,
-             const float* __restrict__ depth, uint64_t* __restrict__ keys) {
-  pdl_wait();
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= R) return;
-  keys[i] = (uint64_t(tiles_sorted[i]) << 32) | __float_as_uint(depth[point_list[i]]);
 }
 
 // Per-tile [start, end) into the sorted list (rasterizer_impl.cu:116-138); ranges is zero-filled.
@@ -607,6 +611,13 @@ mark_visible_kernel(int64_t P, const float* __restrict__ means3D, const float* _
 
 // ---------------------------------------------------------------------------
 // host side
+// Binning mode: super-tile counting (binning.cuh) unless CURVEGS_BINNING=sort or the image has more super-tiles
+// than the chunk tables are sized for.
+static bool bin_by_supertile(int W, int H) {
+  static const bool want = [] { const char* e = getenv("CURVEGS_BINNING"); return !(e && strcmp(e, "sort") == 0); }();
+  const size_t nst = size_t((W + TILE_X * ST_SIDE - 1) / (TILE_X * ST_SIDE)) * ((H + TILE_Y * ST_SIDE - 1) / (TILE_Y * ST_SIDE));
+  return want && nst <= size_t(BIN_MAX_SUPERTILES);
+}
 int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D, const float* opacities,
                     const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
                     const float* all_map, int32_t* radii, void* geom, int64_t* num_rendered, cudaStream_t st) {
@@ -622,7 +633,7 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
                                                  s->render_geo ? all_map : nullptr, radii, g); }
   CG_LAUNCH_CHECK(s->debug, st);
   { StageTimer t_(ST_SCAN, st, 1);
-  launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g); }
+  launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g, 0); }
   CG_LAUNCH_CHECK(s->debug, st);
   // R goes to pinned host memory; the host then waits on an EVENT recorded right behind that copy while the
   // stream already carries the next, R-independent stage (depth sort of the Gaussians + offsets in depth
@@ -651,8 +662,11 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
     rc = radix_sort_pairs<uint32_t>(g.gs, P, 32, &gcur, s->debug != 0, st); }
     if (rc != CG_OK) return rc;
     { StageTimer t_(ST_SCAN, st, 2);
-    launch_k(perm_block_sums, dim3(unsigned(nblk)), dim3(256), 0, st, P, g.gs.vals[gcur], g);
-    launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g); }
+    // offsets, in depth order, of what the binning emits per Gaussian: its tile instances (sort path) or its
+    // super-tile copies (total -> g.total[1])
+    const bool by_st = bin_by_supertile(W, H);
+    launch_k(perm_block_sums, dim3(unsigned(nblk)), dim3(256), 0, st, P, g.gs.vals[gcur], g, by_st ? ST_SHIFT : 0);
+    launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g, by_st ? 1 : 0); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   if (num_rendered) {
@@ -677,13 +691,42 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
   const int64_t nblk = (P + 255) / 256;
   const size_t tiles = size_t(gx) * gy;
 
-  // tile ranges, and behind them the size-class counters of the ring backward
-  CG_CUDA(cudaMemsetAsync(im.ranges, 0, size_t(reinterpret_cast<char*>(im.cls_count + RING_CLASSES + 32) - reinterpret_cast<char*>(im.ranges)), st));
-  if (R > 0) {
+  // tile ranges and, behind them, the size-class counters of the ring backward and the binning's tile counts and
+  // super-tile ranges
+  CG_CUDA(cudaMemsetAsync(im.ranges, 0, size_t(reinterpret_cast<char*>(im.chunk_start) - reinterpret_cast<char*>(im.ranges)), st));
+  const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];   // the Gaussians in depth order (cg_raster_fwd_geom)
+  if (R > 0 && bin_by_supertile(W, H)) {
+    // ---- super-tile binning (binning.cuh) ----
+    int rc, cur = 0;
+    const int sgx = (gx + ST_SIDE - 1) / ST_SIDE, sgy = (gy + ST_SIDE - 1) / ST_SIDE;
+    const uint32_t ns = uint32_t(sgx) * uint32_t(sgy);
+    const int end_bit = int(tile_key_bits(ns));
+    int passes, bpp;
+    radix_sort_geometry(end_bit, 32, &passes, &bpp);
+    const bool fused_hist = passes <= 2;
+    const uint32_t* d_copies = g.total + 1;   // number of copies: only known on the device
+    if (fused_hist) { rc = radix_sort_begin<uint32_t>(bs.is, R, end_bit, st); if (rc != CG_OK) return rc; }
+    { StageTimer t_(ST_EMIT_KEYS, st, 1);
+    launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, sgx, bs.is.keys[0], bs.is.vals[0],
+             uint32_t(R), nr_out, fused_hist ? bs.is.hist : nullptr, bpp, ST_SHIFT); }
+    CG_LAUNCH_CHECK(s->debug, st);
+    { StageTimer t_(ST_SORT, st, 0);
+    rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_copies, fused_hist, nullptr); }
+    if (rc != CG_OK) return rc;
+    const unsigned rb = unsigned(min(int64_t(148 * 16), (R + 1023) / 1024));
+    const unsigned cb = unsigned((BinScratch::max_chunks(R) - BIN_MAX_SUPERTILES + ns + 7) / 8);   // warps: R / BIN_CHUNK + ns + 1
+    { StageTimer t_(ST_TILE_RANGES, st, 6);
+    launch_k(tile_ranges, dim3(rb), dim3(256), 0, st, R, d_copies, bs.is.keys[cur], im.st_ranges);
+    launch_k(bin_chunk_table, dim3(1), dim3(1024), 0, st, ns, im.st_ranges, im.chunk_start);
+    launch_k(bin_count, dim3(cb), dim3(256), 0, st, ns, uint32_t(sgx), im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect, bs.ccnt);
+    launch_k(bin_scan_chunks, dim3(ns), dim3(256), 0, st, uint32_t(sgx), gx, gy, im.chunk_start, bs.ccnt, bs.cbase, im.tile_cnt);
+    launch_k(bin_scan_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles), im.tile_cnt, uint32_t(R), im.ranges);
+    launch_k(bin_fill, dim3(cb), dim3(256), 0, st, ns, uint32_t(sgx), gx, gy, im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect,
+             bs.cbase, im.ranges, uint32_t(R), bk.point_list); }
+    CG_LAUNCH_CHECK(s->debug, st);
+  } else if (R > 0) {
     int rc;
-    // the Gaussians were depth-sorted and their offsets scanned in that order by cg_raster_fwd_geom;
-    // here: one (tile, Gaussian) pair per overlapped tile
-    const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];
+    // ---- sort path: one (tile, Gaussian) pair per overlapped tile, emitted in depth order, ...
     // stable sort by tile only; emit_keys counts the digit histograms of its passes while it writes the keys
     int cur = 0;
     const int end_bit = int(tile_key_bits(uint32_t(tiles)));
@@ -693,7 +736,7 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
     if (fused_hist) { rc = radix_sort_begin<uint32_t>(bs.is, R, end_bit, st); if (rc != CG_OK) return rc; }
     { StageTimer t_(ST_EMIT_KEYS, st, 1);
     launch_k(emit_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, perm, g, gx, bs.is.keys[0], bs.is.vals[0],
-             uint32_t(R), nr_out, fused_hist ? bs.is.hist : nullptr, bpp); }
+             uint32_t(R), nr_out, fused_hist ? bs.is.hist : nullptr, bpp, 0); }
     CG_LAUNCH_CHECK(s->debug, st);
     { StageTimer t_(ST_SORT, st, 0);
     // (its last pass leaves the sorted Gaussian indices directly in the point list that the backward keeps)
@@ -720,16 +763,16 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
   return CG_OK;
 }
 
-int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, const void* bin_keep,
+int launch_rebuild_keys(int64_t P, int64_t R, int W, int H, const void* geom, const void* img, const void* bin_keep,
                         const void* bin_scratch, uint64_t* dst, cudaStream_t st) {
   if (R <= 0) return CG_OK;
   GeomState g = GeomState::carve(const_cast<void*>(geom), P, nullptr);
+  ImgState im = ImgState::carve(const_cast<void*>(img), W, H, nullptr);
   BinKeep bk = BinKeep::carve(const_cast<void*>(bin_keep), R, nullptr);
-  BinScratch bs = BinScratch::carve(const_cast<void*>(bin_scratch), P, R, nullptr);
+  (void)bin_scratch;   // (the tile of an instance follows from the tile ranges; the sorted tile keys are not needed)
   const size_t tiles = size_t((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
-  const int passes = min(4, max(1, (int(tile_key_bits(uint32_t(tiles))) + 7) / 8));
   count_launches(1);
-  launch_k(rebuild_keys, dim3(unsigned((R + 255) / 256)), dim3(256), 0, st, R, bs.is.keys[passes & 1], bk.point_list, g.depth, dst);
+  launch_k(rebuild_keys_ranges, dim3(unsigned(tiles)), dim3(256), 0, st, im.ranges, bk.point_list, g.depth, dst);
   CG_LAUNCH_CHECK(0, st);
   return CG_OK;
 }
