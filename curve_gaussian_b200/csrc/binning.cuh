@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t a, uint32_t lane) 
   return a;
 }
 
-// What a warp needs to walk its chunk.
+// What a CTA needs to walk its chunk: BIN_CHUNK consecutive copies of one super-tile, BIN_WCHUNK per warp.
 struct BinChunk {
   uint32_t s, first, n, ox, oy;
   bool live;
@@ -118,60 +118,76 @@ __device__ __forceinline__ BinChunk bin_locate(uint32_t chunk, uint32_t ns, uint
   return c;
 }
 
-// ccnt[chunk][t] = copies of the chunk that cover tile t of its super-tile.
-__global__ void __launch_bounds__(256)
-bin_count(uint32_t ns, uint32_t sgx, const uint2* __restrict__ st_ranges, const uint32_t* __restrict__ chunk_start,
-          const uint32_t* __restrict__ dup_list, const uint2* __restrict__ rect, uint16_t* __restrict__ ccnt) {
-  pdl_wait();
-  const uint32_t lane = threadIdx.x & 31, chunk = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const BinChunk c = bin_locate(chunk, ns, sgx, st_ranges, chunk_start);
-  if (!c.live) return;
-  uint32_t lo[BIN_EPL], hi[BIN_EPL];
+// The warp's BIN_WCHUNK copies of the chunk as coverage sets per tile: after the transposes lane t holds in m0[e] /
+// m1[e] the copies (bit k = copy e * 32 + k of the warp) that cover tiles t / t + 32 of the super-tile. ids (may be
+// NULL) receives the Gaussian indices of the warp's copies.
+__device__ __forceinline__ void bin_warp_sets(const BinChunk& c, uint32_t warp, uint32_t lane, const uint32_t* __restrict__ dup_list,
+                                              const uint2* __restrict__ rect, uint32_t* ids, uint32_t (&m0)[BIN_EPL],
+                                              uint32_t (&m1)[BIN_EPL]) {
+  const uint32_t w0 = warp * BIN_WCHUNK;
 #pragma unroll
   for (int e = 0; e < BIN_EPL; ++e) {
-    const uint32_t j = e * 32 + lane;
+    const uint32_t j = w0 + e * 32 + lane;
     uint64_t m = 0;
-    if (j < c.n) m = st_mask(rect[dup_list[c.first + j]], c.ox, c.oy);
-    lo[e] = uint32_t(m); hi[e] = uint32_t(m >> 32);
+    if (j < c.n) {
+      const uint32_t id = dup_list[c.first + j];
+      if (ids) ids[e * 32 + lane] = id;
+      m = st_mask(rect[id], c.ox, c.oy);
+    }
+    m0[e] = uint32_t(m); m1[e] = uint32_t(m >> 32);
   }
-  // column sums of the 128 x 64 bit matrix: lane t takes columns t and t + 32 (transpose, then a popcount)
-  uint32_t c0 = 0, c1 = 0;
 #pragma unroll
   for (int e = 0; e < BIN_EPL; ++e) {
-    if (uint32_t(e * 32) >= c.n) break;
-    c0 += __popc(warp_transpose32(lo[e], lane));
-    c1 += __popc(warp_transpose32(hi[e], lane));
+    const bool any = w0 + e * 32 < c.n;   // warp-uniform
+    m0[e] = any ? warp_transpose32(m0[e], lane) : 0u;
+    m1[e] = any ? warp_transpose32(m1[e], lane) : 0u;
   }
-  ccnt[size_t(chunk) * 64 + lane] = uint16_t(c0);
-  ccnt[size_t(chunk) * 64 + 32 + lane] = uint16_t(c1);
 }
 
-// One CTA per super-tile: cbase[chunk][t] = copies covering tile t in the super-tile's earlier chunks;
-// tile_cnt[tile] = the tile's total. Thread = (tile t, one of four contiguous parts of the chunk list).
+// ccnt[chunk][t] = copies of the chunk that cover tile t of its super-tile. One CTA per chunk.
 __global__ void __launch_bounds__(256)
-bin_scan_chunks(uint32_t sgx, int grid_x, int grid_y, const uint32_t* __restrict__ chunk_start,
-                const uint16_t* __restrict__ ccnt, uint32_t* __restrict__ cbase, uint32_t* __restrict__ tile_cnt) {
+bin_count(uint32_t ns, uint32_t sgx, const uint2* __restrict__ st_ranges, const uint32_t* __restrict__ chunk_start,
+          const uint32_t* __restrict__ dup_list, const uint2* __restrict__ rect, uint32_t* __restrict__ ccnt) {
   pdl_wait();
-  __shared__ uint32_t s_part[4][64];
-  const uint32_t s = blockIdx.x, t = threadIdx.x & 63, part = threadIdx.x >> 6;
+  __shared__ uint32_t s_cnt[64];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
+  const BinChunk c = bin_locate(chunk, ns, sgx, st_ranges, chunk_start);
+  if (!c.live) return;
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t m0[BIN_EPL], m1[BIN_EPL];
+  bin_warp_sets(c, warp, lane, dup_list, rect, nullptr, m0, m1);
+  uint32_t c0 = 0, c1 = 0;
+#pragma unroll
+  for (int e = 0; e < BIN_EPL; ++e) { c0 += __popc(m0[e]); c1 += __popc(m1[e]); }
+  if (c0) atomicAdd(&s_cnt[lane], c0);
+  if (c1) atomicAdd(&s_cnt[32 + lane], c1);
+  __syncthreads();
+  if (threadIdx.x < 64) ccnt[size_t(chunk) * 64 + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// One CTA of 64 threads per super-tile: cbase[chunk][t] = copies covering tile t in the super-tile's earlier
+// chunks; tile_cnt[tile] = the tile's total.
+__global__ void __launch_bounds__(64)
+bin_scan_chunks(uint32_t sgx, int grid_x, int grid_y, const uint32_t* __restrict__ chunk_start,
+                const uint32_t* __restrict__ ccnt, uint32_t* __restrict__ cbase, uint32_t* __restrict__ tile_cnt) {
+  pdl_wait();
+  const uint32_t s = blockIdx.x, t = threadIdx.x;
   const uint32_t c0 = chunk_start[s], c1 = chunk_start[s + 1];
   if (c0 == c1) return;   // (tile_cnt is zero-filled)
-  const uint32_t per = (c1 - c0 + 3) / 4;
-  const uint32_t a = min(c1, c0 + part * per), b = min(c1, a + per);
-  uint32_t sum = 0;
-  for (uint32_t c = a; c < b; ++c) sum += ccnt[size_t(c) * 64 + t];
-  s_part[part][t] = sum;
-  __syncthreads();
   uint32_t run = 0;
-  for (uint32_t p = 0; p < part; ++p) run += s_part[p][t];
-  for (uint32_t c = a; c < b; ++c) {
-    cbase[size_t(c) * 64 + t] = run;
-    run += ccnt[size_t(c) * 64 + t];
+  for (uint32_t c = c0; c < c1; c += 4) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (c + k < c1) ? ccnt[size_t(c + k) * 64 + t] : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c + k < c1) cbase[size_t(c + k) * 64 + t] = run;
+      run += v[k];
+    }
   }
-  if (part == 3) {
-    const uint32_t tx = ((s % sgx) << ST_SHIFT) + (t & 7u), ty = ((s / sgx) << ST_SHIFT) + (t >> 3);
-    if (tx < uint32_t(grid_x) && ty < uint32_t(grid_y)) tile_cnt[ty * uint32_t(grid_x) + tx] = run;
-  }
+  const uint32_t tx = ((s % sgx) << ST_SHIFT) + (t & 7u), ty = ((s / sgx) << ST_SHIFT) + (t >> 3);
+  if (tx < uint32_t(grid_x) && ty < uint32_t(grid_y)) tile_cnt[ty * uint32_t(grid_x) + tx] = run;
 }
 
 // One CTA: exclusive scan of the tile totals in tile order -> ranges (empty tiles keep the reference's (0, 0)).
@@ -214,56 +230,86 @@ bin_scan_tiles(uint32_t tiles, const uint32_t* __restrict__ tile_cnt, uint32_t c
   }
 }
 
-// point_list[ranges[tile].x + cbase[chunk][t] + rank inside the chunk] = Gaussian index.
+// point_list[ranges[tile].x + cbase[chunk][t] + rank inside the chunk] = Gaussian index. One CTA per chunk: its
+// instances (about six per copy) are first laid out in shared memory tile by tile, then copied out with consecutive
+// threads on consecutive addresses: a tile's run of the chunk is ~90 entries long, so the stores fill whole sectors
+// (the direct per-lane stores of 4 bytes each cost 32 sectors per instruction and 70 us at 8.8 M instances).
+constexpr int BIN_STAGE = 8192;   // staged instances per CTA; a chunk with more writes straight to global memory
 __global__ void __launch_bounds__(256)
 bin_fill(uint32_t ns, uint32_t sgx, int grid_x, int grid_y, const uint2* __restrict__ st_ranges,
          const uint32_t* __restrict__ chunk_start, const uint32_t* __restrict__ dup_list, const uint2* __restrict__ rect,
          const uint32_t* __restrict__ cbase, const uint2* __restrict__ ranges, uint32_t cap,
          uint32_t* __restrict__ point_list) {
   pdl_wait();
-  __shared__ uint32_t s_id[8][BIN_CHUNK];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x * 8 + warp;
+  __shared__ uint32_t s_stage[BIN_STAGE];
+  __shared__ uint8_t s_tile[BIN_STAGE];
+  __shared__ uint32_t s_id[8][BIN_WCHUNK];
+  __shared__ uint32_t s_wcnt[8][64];     // per warp and tile: count, then offset inside the tile's run
+  __shared__ uint32_t s_loff[65];        // first staged slot of each tile
+  __shared__ uint32_t s_goff[64];        // global position of staged slot i of tile t = s_goff[t] + i
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
   const BinChunk c = bin_locate(chunk, ns, sgx, st_ranges, chunk_start);
   if (!c.live) return;
-  uint32_t lo[BIN_EPL], hi[BIN_EPL];
-#pragma unroll
-  for (int e = 0; e < BIN_EPL; ++e) {
-    const uint32_t j = e * 32 + lane;
-    uint64_t m = 0;
-    if (j < c.n) {
-      const uint32_t id = dup_list[c.first + j];
-      s_id[warp][j] = id;
-      m = st_mask(rect[id], c.ox, c.oy);
-    }
-    lo[e] = uint32_t(m); hi[e] = uint32_t(m >> 32);
-  }
-  __syncwarp();
-  // lane t writes the segments of tiles t and t + 32 of the super-tile
-  uint32_t p0 = cap, p1 = cap;
+  uint32_t m0[BIN_EPL], m1[BIN_EPL];
+  bin_warp_sets(c, warp, lane, dup_list, rect, s_id[warp], m0, m1);
   {
-    const uint32_t tx = c.ox + (lane & 7u), ty0 = c.oy + (lane >> 3), ty1 = ty0 + 4u;
-    if (tx < uint32_t(grid_x) && ty0 < uint32_t(grid_y)) p0 = ranges[ty0 * uint32_t(grid_x) + tx].x + cbase[size_t(chunk) * 64 + lane];
-    if (tx < uint32_t(grid_x) && ty1 < uint32_t(grid_y)) p1 = ranges[ty1 * uint32_t(grid_x) + tx].x + cbase[size_t(chunk) * 64 + 32 + lane];
+    uint32_t c0 = 0, c1 = 0;
+#pragma unroll
+    for (int e = 0; e < BIN_EPL; ++e) { c0 += __popc(m0[e]); c1 += __popc(m1[e]); }
+    s_wcnt[warp][lane] = c0;
+    s_wcnt[warp][32 + lane] = c1;
   }
-  // after the transpose lane t holds, per group of 32 copies, the set of copies that cover its tile: it appends
-  // them in list order
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    // tile t: offsets of the warps inside its run, its run's first staged slot, its segment of the point list
+    const uint32_t t = threadIdx.x;
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t v = s_wcnt[w][t]; s_wcnt[w][t] = tot; tot += v; }
+    uint32_t inc = tot;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= uint32_t(o)) inc += n; }
+    if (t == 31) s_loff[64] = inc;   // (borrowed: total of tiles 0..31)
+    __syncwarp();
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    const uint32_t first = (t >= 32 ? s_loff[64] : 0u) + inc - tot;
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    s_loff[t] = first;
+    if (t == 63) s_loff[64] = first + tot;
+    const uint32_t tx = c.ox + (t & 7u), ty = c.oy + (t >> 3);
+    uint32_t g = cap;
+    if (tx < uint32_t(grid_x) && ty < uint32_t(grid_y)) g = ranges[ty * uint32_t(grid_x) + tx].x + cbase[size_t(chunk) * 64 + t];
+    s_goff[t] = g - first;
+  }
+  __syncthreads();
+  const uint32_t n_inst = s_loff[64];
+  const bool staged = n_inst <= uint32_t(BIN_STAGE);
+  // lane t appends, in list order, the copies that cover its tiles
+  uint32_t p0 = s_loff[lane] + s_wcnt[warp][lane], p1 = s_loff[32 + lane] + s_wcnt[warp][32 + lane];
+  const uint32_t g0 = s_goff[lane], g1 = s_goff[32 + lane];
 #pragma unroll
   for (int e = 0; e < BIN_EPL; ++e) {
-    if (uint32_t(e * 32) >= c.n) break;
-    uint32_t m0 = warp_transpose32(lo[e], lane), m1 = warp_transpose32(hi[e], lane);
     const uint32_t* ids = s_id[warp] + e * 32;
-    while (m0) {
-      const uint32_t k = uint32_t(__ffs(int(m0))) - 1u;
-      m0 &= m0 - 1u;
-      if (p0 < cap) point_list[p0] = ids[k];
+    uint32_t a = m0[e], b = m1[e];
+    while (a) {
+      const uint32_t k = uint32_t(__ffs(int(a))) - 1u;
+      a &= a - 1u;
+      if (staged) { s_stage[p0] = ids[k]; s_tile[p0] = uint8_t(lane); }
+      else if (g0 + p0 < cap) point_list[g0 + p0] = ids[k];
       ++p0;
     }
-    while (m1) {
-      const uint32_t k = uint32_t(__ffs(int(m1))) - 1u;
-      m1 &= m1 - 1u;
-      if (p1 < cap) point_list[p1] = ids[k];
+    while (b) {
+      const uint32_t k = uint32_t(__ffs(int(b))) - 1u;
+      b &= b - 1u;
+      if (staged) { s_stage[p1] = ids[k]; s_tile[p1] = uint8_t(32u + lane); }
+      else if (g1 + p1 < cap) point_list[g1 + p1] = ids[k];
       ++p1;
     }
+  }
+  if (!staged) return;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n_inst; i += 256) {
+    const uint32_t g = s_goff[s_tile[i]] + i;
+    if (g < cap) point_list[g] = s_stage[i];
   }
 }
 

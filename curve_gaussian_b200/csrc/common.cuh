@@ -196,7 +196,8 @@ struct SortBufs {
 constexpr int ST_SHIFT = 3;                    // super-tile = 8 x 8 tiles
 constexpr int ST_SIDE = 1 << ST_SHIFT;
 constexpr int BIN_EPL = 4;                     // copies per lane
-constexpr int BIN_CHUNK = 32 * BIN_EPL;        // copies per chunk (one warp)
+constexpr int BIN_WCHUNK = 32 * BIN_EPL;       // copies per warp
+constexpr int BIN_CHUNK = 8 * BIN_WCHUNK;      // copies per chunk (one CTA of 8 warps)
 constexpr int BIN_MAX_SUPERTILES = 16384;      // (a 16384 x 16384 pixel image); larger images use the sort path
 
 struct GeomState {
@@ -297,7 +298,7 @@ struct BinKeep {
 struct BinScratch {
   SortBufs<uint32_t> is;
   // super-tile binning (binning.cuh): per chunk of BIN_CHUNK copies and tile of its super-tile
-  uint16_t* ccnt;    // [chunks][64] copies of the chunk covering the tile
+  uint32_t* ccnt;    // [chunks][64] copies of the chunk covering the tile
   uint32_t* cbase;   // [chunks][64] the same, summed over the super-tile's earlier chunks
   static size_t max_chunks(int64_t R) { return size_t(R > 0 ? R : 0) / BIN_CHUNK + BIN_MAX_SUPERTILES + 1; }
   static BinScratch carve(void* base, int64_t P, int64_t R, size_t* bytes) {
@@ -305,7 +306,7 @@ struct BinScratch {
     Carver c(base);
     BinScratch b;
     b.is = SortBufs<uint32_t>::carve(c, R);
-    b.ccnt = c.take<uint16_t>(max_chunks(R) * 64);
+    b.ccnt = c.take<uint32_t>(max_chunks(R) * 64);
     b.cbase = c.take<uint32_t>(max_chunks(R) * 64);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return b;

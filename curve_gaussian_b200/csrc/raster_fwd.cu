@@ -714,12 +714,12 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
     rc = radix_sort_pairs<uint32_t>(bs.is, R, end_bit, &cur, s->debug != 0, st, d_copies, fused_hist, nullptr); }
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned(min(int64_t(148 * 16), (R + 1023) / 1024));
-    const unsigned cb = unsigned((BinScratch::max_chunks(R) - BIN_MAX_SUPERTILES + ns + 7) / 8);   // warps: R / BIN_CHUNK + ns + 1
+    const unsigned cb = unsigned(BinScratch::max_chunks(R) - BIN_MAX_SUPERTILES + ns);   // chunks: at most R / BIN_CHUNK + ns + 1
     { StageTimer t_(ST_TILE_RANGES, st, 6);
     launch_k(tile_ranges, dim3(rb), dim3(256), 0, st, R, d_copies, bs.is.keys[cur], im.st_ranges);
     launch_k(bin_chunk_table, dim3(1), dim3(1024), 0, st, ns, im.st_ranges, im.chunk_start);
     launch_k(bin_count, dim3(cb), dim3(256), 0, st, ns, uint32_t(sgx), im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect, bs.ccnt);
-    launch_k(bin_scan_chunks, dim3(ns), dim3(256), 0, st, uint32_t(sgx), gx, gy, im.chunk_start, bs.ccnt, bs.cbase, im.tile_cnt);
+    launch_k(bin_scan_chunks, dim3(ns), dim3(64), 0, st, uint32_t(sgx), gx, gy, im.chunk_start, bs.ccnt, bs.cbase, im.tile_cnt);
     launch_k(bin_scan_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles), im.tile_cnt, uint32_t(R), im.ranges);
     launch_k(bin_fill, dim3(cb), dim3(256), 0, st, ns, uint32_t(sgx), gx, gy, im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect,
              bs.cbase, im.ranges, uint32_t(R), bk.point_list); }
