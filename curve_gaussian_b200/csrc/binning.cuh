@@ -45,9 +45,21 @@ __device__ __forceinline__ uint64_t st_mask(uint2 rc, uint32_t ox, uint32_t oy) 
 }
 
 // chunk_start[s] = first chunk of super-tile s; chunk_start[ns] = number of chunks. One CTA.
+// digit_base != NULL (at most 256 super-tiles, i.e. a single sort pass whose digit IS the super-tile index): the
+// super-tile spans are read off the sort's exclusive digit bases (n_copies = total, clamped to cap) and written to
+// st_ranges here, instead of being recovered from the sorted keys by tile_ranges.
 __global__ void __launch_bounds__(1024)
-bin_chunk_table(uint32_t ns, const uint2* __restrict__ st_ranges, uint32_t* __restrict__ chunk_start) {
+bin_chunk_table(uint32_t ns, uint2* __restrict__ st_ranges, uint32_t* __restrict__ chunk_start,
+                const uint32_t* __restrict__ digit_base, const uint32_t* __restrict__ n_copies, uint32_t cap) {
   pdl_wait();
+  if (digit_base) {
+    const uint32_t n = min(*n_copies, cap);
+    for (uint32_t i = threadIdx.x; i < ns; i += 1024) {
+      const uint32_t a = digit_base[i], b = (i + 1 < 256u) ? digit_base[i + 1] : n;
+      st_ranges[i] = make_uint2(a, b);
+    }
+    __syncthreads();
+  }
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -190,12 +202,11 @@ bin_scan_chunks(uint32_t sgx, int grid_x, int grid_y, const uint32_t* __restrict
   if (tx < uint32_t(grid_x) && ty < uint32_t(grid_y)) tile_cnt[ty * uint32_t(grid_x) + tx] = run;
 }
 
-// One CTA: exclusive scan of the tile totals in tile order -> ranges (empty tiles keep the reference's (0, 0)).
+// One CTA (bin_scan_tiles_order in raster_fwd.cu): exclusive scan of the tile totals in tile order -> ranges (empty tiles keep the reference's (0, 0)).
 // cap bounds every range (capacity mode: an overflowing frame is flagged and re-run by the caller, but must stay
 // inside its buffers).
-__global__ void __launch_bounds__(1024)
-bin_scan_tiles(uint32_t tiles, const uint32_t* __restrict__ tile_cnt, uint32_t cap, uint2* __restrict__ ranges) {
-  pdl_wait();
+__device__ __forceinline__ void bin_scan_tiles_body(uint32_t tiles, const uint32_t* __restrict__ tile_cnt, uint32_t cap,
+                                                    uint2* __restrict__ ranges) {
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   if (threadIdx.x == 0) s_carry = 0;

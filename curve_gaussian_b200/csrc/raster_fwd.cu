@@ -44,7 +44,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
   __syncthreads();
 
   const int64_t idx = blk0 + threadIdx.x;
-  uint32_t touched = 0;
+  uint32_t touched = 0, depth_key = 0xffffffffu;
   int radius_out = 0;
   if (idx < P) {
     const float px = s_mean[3 * threadIdx.x], py = s_mean[3 * threadIdx.x + 1], pz = s_mean[3 * threadIdx.x + 2];
@@ -96,6 +96,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
           touched = area;
           radius_out = rad;
           g.depth[idx] = p_view.z;
+          depth_key = __float_as_uint(p_view.z);
           // the record the blend kernels gather by Gaussian index: three 16-byte stores
           float4* rec = reinterpret_cast<float4*>(g.grec + idx);
           rec[0] = make_float4(conic.x, conic.y, conic.z, 1.f / p_view.z);
@@ -107,6 +108,10 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
     }
     radii[idx] = radius_out;
     g.tiles[idx] = touched;
+    // input of the depth sort: key = bits of the view-space depth (culled Gaussians emit nothing, their key only
+    // has to be deterministic), value = Gaussian index
+    g.gs.keys[0][idx] = depth_key;
+    g.gs.vals[0][idx] = uint32_t(idx);
   }
   // block sum of tiles_touched -> blk_sum
   uint32_t v = touched;
@@ -154,17 +159,6 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
     __syncthreads();
   }
   if (threadIdx.x == 0) g.total[slot] = s_carry;
-}
-
-// Per-Gaussian sort input: key = bits of the view-space depth (culled Gaussians emit nothing,
-// their key only has to be deterministic), value = Gaussian index.
-__global__ void __launch_bounds__(256)
-init_depth_keys(int64_t P, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  pdl_wait();
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= P) return;
-  keys[i] = g.tiles[i] ? __float_as_uint(g.depth[i]) : 0xffffffffu;
-  vals[i] = uint32_t(i);
 }
 
 // Block sums of tiles_touched (shift = 0) or of the number of super-tiles overlapped (shift = ST_SHIFT), taken in
@@ -314,10 +308,9 @@ constexpr int BATCH = BLEND_THREADS;
 // tail is made of short ones instead of whichever tiles happen to sit in the last image rows.
 // ntiles counts blend CTAs (tile * BLEND_SUBS + sub). Lengths: the tile's range (end - start) when maxc is
 // NULL, else maxc (what the backward walks).
-__global__ void __launch_bounds__(1024)
-order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ maxc,
-            uint32_t* __restrict__ tile_order) {
-  pdl_wait();
+// (lens != NULL: the lengths themselves, one per tile)
+__device__ __forceinline__ void order_tiles_body(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ maxc,
+                                                 const uint32_t* __restrict__ lens, uint32_t* __restrict__ tile_order) {
   __shared__ uint32_t s_cnt[1024];
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_max;
@@ -325,7 +318,7 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* _
   s_cnt[tid] = 0;
   if (tid == 0) s_max = 1;
   __syncthreads();
-  auto length = [&](uint32_t t) { if (maxc) return maxc[t]; const uint2 r = ranges[t / BLEND_SUBS]; return r.y - r.x; };
+  auto length = [&](uint32_t t) { if (lens) return lens[t / BLEND_SUBS]; if (maxc) return maxc[t]; const uint2 r = ranges[t / BLEND_SUBS]; return r.y - r.x; };
   // every pass reads the lengths in batches of 8 independent loads per thread (one CTA: latency, not bandwidth)
   uint32_t mx = 0;
   for (uint32_t base = 0; base < ntiles; base += 8192) {
@@ -374,6 +367,22 @@ order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* _
       if (t < ntiles) tile_order[atomicAdd(&s_cnt[bucket(len[k])], 1u)] = t;   // order inside a bucket is irrelevant
     }
   }
+}
+__global__ void __launch_bounds__(1024)
+order_tiles(uint32_t ntiles, const uint2* __restrict__ ranges, const uint32_t* __restrict__ maxc,
+            uint32_t* __restrict__ tile_order) {
+  pdl_wait();
+  order_tiles_body(ntiles, ranges, maxc, nullptr, tile_order);
+}
+// Super-tile binning: the single CTA that scans the tile totals into the tile ranges also has the list lengths at
+// hand, so it orders the blend CTAs too (one launch and one pass over the ranges less).
+__global__ void __launch_bounds__(1024)
+bin_scan_tiles_order(uint32_t tiles, const uint32_t* __restrict__ tile_cnt, uint32_t cap, uint2* __restrict__ ranges,
+                     uint32_t* __restrict__ tile_order) {
+  pdl_wait();
+  bin_scan_tiles_body(tiles, tile_cnt, cap, ranges);
+  __syncthreads();
+  order_tiles_body(tiles * BLEND_SUBS, nullptr, nullptr, tile_cnt, tile_order);
 }
 
 // One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block.
@@ -656,9 +665,7 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
   }
   {
     int rc, gcur = 0;
-    { StageTimer t_(ST_SORT, st, 1);
-    launch_k(init_depth_keys, dim3(unsigned(nblk)), dim3(256), 0, st, P, g, g.gs.keys[0], g.gs.vals[0]);
-    CG_LAUNCH_CHECK(s->debug, st);
+    { StageTimer t_(ST_SORT, st, 0);
     rc = radix_sort_pairs<uint32_t>(g.gs, P, 32, &gcur, s->debug != 0, st); }
     if (rc != CG_OK) return rc;
     { StageTimer t_(ST_SCAN, st, 2);
@@ -695,7 +702,8 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
   // super-tile ranges
   CG_CUDA(cudaMemsetAsync(im.ranges, 0, size_t(reinterpret_cast<char*>(im.chunk_start) - reinterpret_cast<char*>(im.ranges)), st));
   const uint32_t* perm = g.gs.vals[radix_sort_result_buf(32)];   // the Gaussians in depth order (cg_raster_fwd_geom)
-  if (R > 0 && bin_by_supertile(W, H)) {
+  const bool by_st = R > 0 && bin_by_supertile(W, H);
+  if (by_st) {
     // ---- super-tile binning (binning.cuh) ----
     int rc, cur = 0;
     const int sgx = (gx + ST_SIDE - 1) / ST_SIDE, sgy = (gy + ST_SIDE - 1) / ST_SIDE;
@@ -715,12 +723,14 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
     if (rc != CG_OK) return rc;
     const unsigned rb = unsigned(min(int64_t(148 * 16), (R + 1023) / 1024));
     const unsigned cb = unsigned(BinScratch::max_chunks(R) - BIN_MAX_SUPERTILES + ns);   // chunks: at most R / BIN_CHUNK + ns + 1
-    { StageTimer t_(ST_TILE_RANGES, st, 6);
-    launch_k(tile_ranges, dim3(rb), dim3(256), 0, st, R, d_copies, bs.is.keys[cur], im.st_ranges);
-    launch_k(bin_chunk_table, dim3(1), dim3(1024), 0, st, ns, im.st_ranges, im.chunk_start);
+    const bool spans_from_hist = fused_hist && passes == 1;   // (up to 256 super-tiles: 2048 x 2048 pixels)
+    { StageTimer t_(ST_TILE_RANGES, st, spans_from_hist ? 4 : 5);
+    if (!spans_from_hist) launch_k(tile_ranges, dim3(rb), dim3(256), 0, st, R, d_copies, bs.is.keys[cur], im.st_ranges);
+    launch_k(bin_chunk_table, dim3(1), dim3(1024), 0, st, ns, im.st_ranges, im.chunk_start,
+             spans_from_hist ? bs.is.hist : nullptr, d_copies, uint32_t(R));
     launch_k(bin_count, dim3(cb), dim3(256), 0, st, ns, uint32_t(sgx), im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect, bs.ccnt);
     launch_k(bin_scan_chunks, dim3(ns), dim3(64), 0, st, uint32_t(sgx), gx, gy, im.chunk_start, bs.ccnt, bs.cbase, im.tile_cnt);
-    launch_k(bin_scan_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles), im.tile_cnt, uint32_t(R), im.ranges);
+    launch_k(bin_scan_tiles_order, dim3(1), dim3(1024), 0, st, uint32_t(tiles), im.tile_cnt, uint32_t(R), im.ranges, im.tile_order);
     launch_k(bin_fill, dim3(cb), dim3(256), 0, st, ns, uint32_t(sgx), gx, gy, im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect,
              bs.cbase, im.ranges, uint32_t(R), bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
@@ -748,8 +758,8 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
     CG_LAUNCH_CHECK(s->debug, st);
   }
   const dim3 grid{unsigned(tiles) * BLEND_SUBS, 1u, 1u}, block{unsigned(BLEND_THREADS), 1u, 1u};
-  StageTimer t_blend(ST_BLEND_FWD, st, 2);
-  launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
+  StageTimer t_blend(ST_BLEND_FWD, st, by_st ? 1 : 2);
+  if (!by_st) launch_k(order_tiles, dim3(1), dim3(1024), 0, st, uint32_t(tiles) * BLEND_SUBS, im.ranges, nullptr, im.tile_order);
   CG_LAUNCH_CHECK(s->debug, st);
   if (s->render_geo)
     launch_k(blend_fwd<true>, dim3(grid), dim3(block), 0, st, im.ranges, im.tile_order, gx, g.grec, bk.point_list, W, H, s->bg,
