@@ -6,6 +6,7 @@ Bars (BASELINE.json north_star): bit-exact radii / tile counts / sort keys /
 point list / tile ranges / n_contrib; <= 1e-5 max-rel on pixels and gradients.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -112,9 +113,18 @@ def make_case(name, dev):
         opac[2700:2800] = 1.0 / 255.0
         opac[2800:2900] = 1.0
         opac[2900:2950] = 0.003
+    elif name == "wide_many_supertiles":
+        # 264 x 65 tiles = 33 x 9 = 297 super-tiles: more than one sort digit, so the binning takes its super-tile
+        # spans from the sorted keys (not from the digit bases) and sorts the copies in two passes; a few splats
+        # span dozens of super-tiles, most sit inside one
+        W, H, P = 4224, 1040, 12000
+        means, scales, rots, opac, colors, amap = synth.random_gaussians(P, seed=21, scale_lo=0.002, scale_hi=0.03)
+        scales[:6] = 1.5
+        opac[:6] = 0.05
     else:
         raise KeyError(name)
-    seed = {"cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14, "ties_and_extremes": 15}[name]
+    seed = {"cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14, "ties_and_extremes": 15,
+            "wide_many_supertiles": 16}[name]
     cam = synth.random_cameras(1, W, H, seed=seed)[0].to(dev)
     t = lambda x: x.to(dev).contiguous()
     return cam, t(means), t(scales), t(rots), t(opac), t(colors), t(amap)
@@ -270,9 +280,12 @@ def test_mark_visible_matches_reference(cuda_dev):
                   visible=int(theirs.sum()), bit_identical=True)
 
 
-@pytest.mark.parametrize("case", ["cloud_small", "cloud_dense", "discs", "behind_and_offscreen", "ties_and_extremes"])
+@pytest.mark.parametrize("case", ["cloud_small", "cloud_dense", "discs", "behind_and_offscreen", "ties_and_extremes",
+                                  "wide_many_supertiles"])
 @pytest.mark.parametrize("bg_val", [0.0, 0.3])
 def test_forward_backward_match_reference(cuda_dev, case, bg_val):
+    if case == "wide_many_supertiles" and bg_val != 0.0:
+        pytest.skip("one background is enough for the 4.4 Mpixel case")
     if refload.ref_rasterizer() is None:
         pytest.skip("oracle/_ref/diff_cur_rasterization_C.so not built")
     dev = cuda_dev
@@ -357,3 +370,16 @@ def test_color_only_backward_skips_unused_channels(cuda_dev):
     torch.cuda.synchronize()
     for i in (0, 1, 2, 3, 6, 7, 8):
         assert max_rel(bw[i], bw_ref[i]) <= GRAD_TOL, i
+
+
+def test_sort_path_binning_matches_golden():
+    """CURVEGS_BINNING=sort (the R-sized tile sort kept as the fallback for images with more than 16384 super-tiles,
+    and as the A/B yardstick of the super-tile binning) is chosen once per process: run the golden-vector test file
+    in a child process with it."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CURVEGS_BINNING="sort")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_raster_golden.py", "-q", "-m", "gpu", "-x"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
