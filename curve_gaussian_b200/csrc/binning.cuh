@@ -162,20 +162,24 @@ bin_count(uint32_t ns, uint32_t sgx, const uint2* __restrict__ st_ranges, const 
           const uint32_t* __restrict__ dup_list, const uint2* __restrict__ rect, uint32_t* __restrict__ ccnt) {
   pdl_wait();
   __shared__ uint32_t s_cnt[64];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
-  const BinChunk c = bin_locate(chunk, ns, sgx, st_ranges, chunk_start);
-  if (!c.live) return;
-  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  uint32_t m0[BIN_EPL], m1[BIN_EPL];
-  bin_warp_sets(c, warp, lane, dup_list, rect, nullptr, m0, m1);
-  uint32_t c0 = 0, c1 = 0;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (a fixed grid strides over the chunks: their number is only known on the device)
+  for (uint32_t chunk = blockIdx.x;; chunk += gridDim.x) {
+    const BinChunk c = bin_locate(chunk, ns, sgx, st_ranges, chunk_start);
+    if (!c.live) return;
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t m0[BIN_EPL], m1[BIN_EPL];
+    bin_warp_sets(c, warp, lane, dup_list, rect, nullptr, m0, m1);
+    uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-  for (int e = 0; e < BIN_EPL; ++e) { c0 += __popc(m0[e]); c1 += __popc(m1[e]); }
-  if (c0) atomicAdd(&s_cnt[lane], c0);
-  if (c1) atomicAdd(&s_cnt[32 + lane], c1);
-  __syncthreads();
-  if (threadIdx.x < 64) ccnt[size_t(chunk) * 64 + threadIdx.x] = s_cnt[threadIdx.x];
+    for (int e = 0; e < BIN_EPL; ++e) { c0 += __popc(m0[e]); c1 += __popc(m1[e]); }
+    if (c0) atomicAdd(&s_cnt[lane], c0);
+    if (c1) atomicAdd(&s_cnt[32 + lane], c1);
+    __syncthreads();
+    if (threadIdx.x < 64) ccnt[size_t(chunk) * 64 + threadIdx.x] = s_cnt[threadIdx.x];
+    __syncthreads();
+  }
 }
 
 // One CTA of 64 threads per super-tile: cbase[chunk][t] = copies covering tile t in the super-tile's earlier
@@ -258,7 +262,8 @@ bin_fill(uint32_t ns, uint32_t sgx, int grid_x, int grid_y, const uint2* __restr
   __shared__ uint32_t s_wcnt[8][64];     // per warp and tile: count, then offset inside the tile's run
   __shared__ uint32_t s_loff[65];        // first staged slot of each tile
   __shared__ uint32_t s_goff[64];        // global position of staged slot i of tile t = s_goff[t] + i
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t chunk = blockIdx.x;; chunk += gridDim.x) {   // (fixed grid: the number of chunks is only known on the device)
   const BinChunk c = bin_locate(chunk, ns, sgx, st_ranges, chunk_start);
   if (!c.live) return;
   uint32_t m0[BIN_EPL], m1[BIN_EPL];
@@ -316,11 +321,14 @@ bin_fill(uint32_t ns, uint32_t sgx, int grid_x, int grid_y, const uint2* __restr
       ++p1;
     }
   }
-  if (!staged) return;
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n_inst; i += 256) {
-    const uint32_t g = s_goff[s_tile[i]] + i;
-    if (g < cap) point_list[g] = s_stage[i];
+  if (staged) {
+    for (uint32_t i = threadIdx.x; i < n_inst; i += 256) {
+      const uint32_t g = s_goff[s_tile[i]] + i;
+      if (g < cap) point_list[g] = s_stage[i];
+    }
+  }
+  __syncthreads();   // (the shared arrays are rewritten by the next chunk)
   }
 }
 

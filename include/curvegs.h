@@ -80,10 +80,11 @@ typedef struct cg_raster_settings {
 
 /* Sizes of the opaque state buffers the caller must allocate (bytes).
  * geom: per-Gaussian state (one 48-byte record per Gaussian that the blend kernels gather by index, depth,
- * tile counts / rects, and the depth-sort buffers of the P Gaussians), img: per-pixel / per-tile / per-8x4-block
+ * tile counts / rects, and the depth-sort buffers of the P Gaussians), img: per-pixel / per-tile / per-4x4-block
  * state, both saved for backward. bin_keep: the point list (sorted Gaussian index per tile-instance) and the
- * per-block candidate lists the forward leaves for the ring backward, saved for backward.
- * bin_scratch: sort double buffers of the R instances, only live during forward. */
+ * per-block contributor lists the forward leaves for the ring backward, saved for backward.
+ * bin_scratch: working buffers of the tile binning (sort buffers, per-chunk tile counts), only live during
+ * forward. */
 size_t cg_raster_geom_bytes(int64_t P);
 size_t cg_raster_img_bytes(int32_t W, int32_t H);
 size_t cg_raster_bin_keep_bytes(int64_t R);

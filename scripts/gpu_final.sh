@@ -19,9 +19,9 @@ timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 7
   python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline --no-small-scene --no-reference-step > $OUT/ncu_launch_bench.log 2>&1
 # one --set full pass over the kernels that make up >90 % of the step (FULL=1: every libcurvegs kernel of one step)
 if [ "${FULL:-0}" = "1" ]; then
-  KRE='^(activate_|blend_|emit_keys|tile_ranges|init_depth_keys|perm_block_sums|preprocess_fwd|preprocess_bwd|sample_|scan_block_sums|sort_|ssim_)'; SKIP=200; CNT=40
+  KRE='^(activate_|blend_|bin_|emit_keys|tile_ranges|perm_block_sums|preprocess_fwd|preprocess_bwd|sample_|scan_block_sums|sort_|ssim_)'; SKIP=200; CNT=42
 else
-  KRE='^(blend_|tile_ranges|sort_onesweep|preprocess_fwd|preprocess_bwd|sample_bwd_point|ssim_fwd|emit_keys)'; SKIP=60; CNT=14
+  KRE='^(blend_|bin_fill|bin_count|sort_onesweep|preprocess_fwd|preprocess_bwd|sample_bwd_point|ssim_fwd|emit_keys)'; SKIP=60; CNT=14
 fi
 timeout -k 10 500 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s $SKIP -c $CNT -o $OUT/full \
   python bench.py --steps 2 --warmup 3 --views 2 --no-cpu-baseline --no-small-scene --no-reference-step > $OUT/ncu_full_bench.log 2>&1
