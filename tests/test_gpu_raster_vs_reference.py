@@ -119,8 +119,10 @@ def make_case(name, dev):
         # span dozens of super-tiles, most sit inside one
         W, H, P = 4224, 1040, 12000
         means, scales, rots, opac, colors, amap = synth.random_gaussians(P, seed=21, scale_lo=0.002, scale_hi=0.03)
-        scales[:4] = 0.4       # (kept moderate: the fp32-atomic noise of a gradient summed over millions of pixels
-        opac[:4] = 0.05        #  is what the reference-vs-reference floor of this comparison measures)
+        # (a dozen super-tiles across; not screen-filling: the covariance gradient of a splat summed over millions of
+        #  pixels is ill-conditioned, and its fp32-atomic noise - not the binning - would decide the comparison)
+        scales[:4] = 0.12
+        opac[:4] = 0.05
     else:
         raise KeyError(name)
     seed = {"cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14, "ties_and_extremes": 15,
