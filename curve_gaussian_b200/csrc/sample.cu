@@ -147,6 +147,31 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
+// Four fp64 block sums at once, added to sums[0..3]. A plain butterfly moves every double through five shuffle
+// steps (two SHFLs + packing each: a quarter of sample_bwd_point's instructions); here the first two steps halve
+// the number of values a lane still carries (lanes keep sums {0,1} or {2,3}, then one of the pair), so 12 SHFLs and 6
+// DADDs per warp instead of 40 and 20. sm: 8 x 4 doubles.
+__device__ __forceinline__ void block_sum4_add(double (&v)[4], double* sm, double* __restrict__ sums) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool h4 = (lane & 16u) != 0u, h3 = (lane & 8u) != 0u;
+  double k0 = h4 ? v[2] : v[0], k1 = h4 ? v[3] : v[1];
+  k0 += __shfl_xor_sync(0xffffffffu, h4 ? v[0] : v[2], 16);
+  k1 += __shfl_xor_sync(0xffffffffu, h4 ? v[1] : v[3], 16);
+  double k = h3 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, h3 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  // lanes 0, 8, 16, 24 now hold the warp's sums 0, 1, 2, 3
+  if ((lane & 7u) == 0u) sm[warp * 4 + (lane >> 3)] = k;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t += sm[w * 4 + threadIdx.x];
+    atomicAdd(&sums[threadIdx.x], t);
+  }
+}
+
 // sums[0] = sum |a|^2, sums[1] = sum |tau x a|^2
 __global__ void __launch_bounds__(256)
 sample_reduce_fwd(int64_t B, int n, const float* __restrict__ cp, const uint8_t* __restrict__ is_bezier,
@@ -242,7 +267,7 @@ sample_bwd_point(int64_t B, int n, const float* __restrict__ cp, const uint8_t* 
                  const float* __restrict__ dL_dxyz, const float* __restrict__ dL_drot,
                  const float* __restrict__ dL_dscaling, float* __restrict__ pt, double* __restrict__ sums) {
   pdl_wait();
-  __shared__ double s_red[8];
+  __shared__ double s_red[32];
   const int64_t P = B * n;
   const int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const float N1 = norms[0], N2 = norms[1];
@@ -296,16 +321,11 @@ sample_bwd_point(int64_t B, int n, const float* __restrict__ cp, const uint8_t* 
 #pragma unroll
     for (int i = 0; i < SB_PT; ++i) pt[int64_t(i) * P + g] = o[i];
   }
-  if (dL_drot) {
-    for (int i = 0; i < 4; ++i) {
-      const double t = block_sum(s[i], s_red);
-      if (threadIdx.x == 0) atomicAdd(&sums[i], t);
-    }
-  }
+  if (dL_drot) block_sum4_add(s, s_red, sums);
 }
 
 // One warp per curve; lanes stride over the curve's samples (coalesced reads of the scratch).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)   // (85 registers: the kernel is bound by the latency of its 4 load rounds per warp, so by occupancy)
 sample_bwd_curve(int64_t B, int n, const float* __restrict__ width, const uint8_t* __restrict__ is_bezier,
                  const float* __restrict__ tt, float half_step, const float* __restrict__ norms,
                  const double* __restrict__ sums, const float* __restrict__ pt, const float* __restrict__ dL_dscaling,
