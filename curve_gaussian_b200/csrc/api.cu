@@ -167,6 +167,8 @@ int cg_raster_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void*
   int rc = check_settings(s);
   if (rc) return rc;
   CG_ARG(P >= 0 && R >= 0, "P/R");
+  // (the per-block contributor lists are addressed with 32-bit offsets of up to 16 * R)
+  CG_ARG(R < (int64_t(1) << 28), "num_rendered must be below 2^28 tile instances");
   CG_ARG(img && out_color && out_invdepth, "img/out_color/out_invdepth");
   CG_ARG(!s->render_geo || out_all_map, "out_all_map required with render_geo");
   CG_ARG((reinterpret_cast<uintptr_t>(img) & 127u) == 0, "img must be 128-byte aligned");
@@ -188,7 +190,7 @@ int cg_raster_fwd_capacity(const cg_raster_settings* s, int64_t P, int64_t R_cap
   int rc = check_settings(s);
   if (rc) return rc;
   CG_ARG(P > 0 && P < (int64_t(1) << 31), "P");
-  CG_ARG(R_cap > 0 && R_cap < (int64_t(1) << 30), "R_cap");
+  CG_ARG(R_cap > 0 && R_cap < (int64_t(1) << 28), "R_cap");   // (32-bit offsets of up to 16 * R into the contributor lists)
   CG_ARG(means3D && opacities && radii && geom && img && colors, "means3D/opacities/radii/geom/img/colors");
   CG_ARG((scales && rotations && !cov3D_precomp) || (!scales && !rotations && cov3D_precomp),
          "exactly one of scale/rotation pair or precomputed 3D covariance");
