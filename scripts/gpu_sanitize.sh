@@ -10,3 +10,6 @@ echo "=== racecheck"
 timeout -k 10 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_raster_golden.py -x -q -m gpu 2>&1 | tail -3
 echo "=== memcheck: capacity binning + CUDA-graph capture / replay (round 1: the capture failed under the sanitizer)"
 timeout -k 10 500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_capacity_graph.py -x -q -m gpu 2>&1 | tail -5
+echo "=== memcheck: binning edge cases against the reference rasterizer (297 super-tiles, unstaged fill, ties / screen-filling splats)"
+timeout -k 10 500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_raster_vs_reference.py -x -q -m gpu \
+  -k "(big_splats or wide or ties) and forward_backward" 2>&1 | tail -4

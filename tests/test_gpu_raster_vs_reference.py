@@ -123,9 +123,16 @@ def make_case(name, dev):
         #  pixels is ill-conditioned, and its fp32-atomic noise - not the binning - would decide the comparison)
         scales[:4] = 0.12
         opac[:4] = 0.05
+    elif name == "big_splats_unstaged_fill":
+        # every splat covers most of the image: a 1024-copy chunk of a super-tile then holds tens of thousands of
+        # instances, more than the binning's fill kernel stages in shared memory, so it takes its direct-store path;
+        # low opacities keep every pixel blending deep into the lists (forward state only: see the test)
+        W, H, P = 256, 256, 3000
+        means, scales, rots, opac, colors, amap = synth.random_gaussians(P, seed=31, scale_lo=0.25, scale_hi=0.5)
+        opac = opac * 0.02 + 0.004
     else:
         raise KeyError(name)
-    seed = {"cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14, "ties_and_extremes": 15,
+    seed = {"big_splats_unstaged_fill": 17, "cloud_small": 11, "cloud_dense": 12, "discs": 13, "behind_and_offscreen": 14, "ties_and_extremes": 15,
             "wide_many_supertiles": 16}[name]
     cam = synth.random_cameras(1, W, H, seed=seed)[0].to(dev)
     t = lambda x: x.to(dev).contiguous()
@@ -283,11 +290,11 @@ def test_mark_visible_matches_reference(cuda_dev):
 
 
 @pytest.mark.parametrize("case", ["cloud_small", "cloud_dense", "discs", "behind_and_offscreen", "ties_and_extremes",
-                                  "wide_many_supertiles"])
+                                  "wide_many_supertiles", "big_splats_unstaged_fill"])
 @pytest.mark.parametrize("bg_val", [0.0, 0.3])
 def test_forward_backward_match_reference(cuda_dev, case, bg_val):
-    if case == "wide_many_supertiles" and bg_val != 0.0:
-        pytest.skip("one background is enough for the 4.4 Mpixel case")
+    if case in ("wide_many_supertiles", "big_splats_unstaged_fill") and bg_val != 0.0:
+        pytest.skip("one background is enough for this case")
     if refload.ref_rasterizer() is None:
         pytest.skip("oracle/_ref/diff_cur_rasterization_C.so not built")
     dev = cuda_dev
@@ -337,6 +344,9 @@ def test_forward_backward_match_reference(cuda_dev, case, bg_val):
         assert max_rel(a, b) <= PIX_TOL, name
     fT = fetch(8, P, R, W, H, geom, img, bin_keep, scratch, torch.float32, W * H)
     assert max_rel(fT, dec["accum_alpha"]) <= PIX_TOL
+
+    if case == "big_splats_unstaged_fill":
+        return   # (a binning case; gradients of image-sized splats are ill-conditioned sums over every pixel)
 
     # ---- gradients
     bw = rasterize_backward_raw(rs, means, radii, colors, amap, opac, scales, rots, None, g_color, g_invd, g_map,
