@@ -2,21 +2,22 @@
 //
 // blend_bwd (raster_bwd.cu) maps lanes to pixels, so every (8x4 block, instance) pair ends in a 32-lane
 // reduction of 8 terms plus 8 atomics: about a third of its instructions. Here the roles are swapped: a
-// lane owns one INSTANCE of its block's candidate list (written by blend_fwd) for 32 consecutive steps and
-// accumulates that instance's gradient sums in registers, while the 32 PIXELS of the block travel around
-// the warp, one lane per step, carrying their blend state (T, the colour seen behind, dL/dpixel, n_contrib,
-// coordinates) in a shuffle ring. Pixel p meets the instances in list order back to front, exactly as in
-// the reference's per-pixel loop, so every per-pixel quantity (T / (1 - alpha) chain, accum_rec recursion,
-// alpha, G) has the same bits; only the order of the sum over pixels differs. There is no cross-lane
-// reduction at all, and one instance ends in two 128-bit vector reductions (REDG.F32x4).
+// lane owns one INSTANCE of a 4x4 pixel block's contributor list (written by blend_fwd: the instances blended
+// into at least one pixel of the block) for 16 consecutive steps and accumulates that instance's gradient sums in
+// registers, while the 16 PIXELS of the block travel around a ring of 16 lanes, one lane per step, carrying their
+// blend state (T, the colour seen behind, dL/dpixel, n_contrib, coordinates) in shuffles. A warp runs two such
+// rings (lanes 0-15 and 16-31) over independent block streams. Pixel p meets the instances in list order back to
+// front, exactly as in the reference's per-pixel loop, so every per-pixel quantity (T / (1 - alpha) chain,
+// accum_rec recursion, alpha, G) has the same bits; only the order of the sum over pixels differs. There is no
+// cross-lane reduction at all, and one instance ends in two 128-bit vector reductions (REDG.F32x4).
 //
-// The ring never drains between blocks: a warp walks the concatenation of the candidate lists of all the
-// blocks assigned to it. Lane i owns sequence elements i, i+32, ... ("epoch" m = elements 32m..32m+31) and
-// switches to its next element at step 32m+i, when pixel 0 arrives; an element flagged as the first of its
-// block re-initialises every pixel slot that reaches it from that block's pixel table. Everything that is
-// not per step happens at the epoch boundaries, for all lanes at once: candidate positions are loaded two
-// epochs ahead, the 32-byte records one epoch ahead (cp.async from the per-Gaussian table straight into the lane's staging slot), the
-// sums of finished instances are flushed one epoch late.
+// A ring never drains between blocks: it walks the concatenation of the lists of all the blocks assigned to it.
+// Lane i of a ring owns sequence elements i, i+16, ... ("epoch" m = elements 16m..16m+15) and switches to its next
+// element at step 16m+i, when pixel 0 arrives; an element flagged as the first of its block re-initialises every
+// pixel slot that reaches it from that block's pixel table. Everything that is not per step happens at the epoch
+// boundaries, for all lanes at once: list positions are loaded two epochs ahead, the 32-byte records one epoch
+// ahead (cp.async from the per-Gaussian table straight into the lane's staging slot), the sums of finished
+// instances are flushed one epoch late.
 //
 // Gradient sums kept per instance (q = o * G * dL/dalpha, d = mean2D - pixel):
 //   S0 = sum G dL/dalpha           -> dL/dopacity
@@ -102,9 +103,9 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
   const unsigned hmask = 0xffffu << hbase;
   const int src = int(hbase | ((hl + 15u) & 15u));
 
-  // ---- this warp's blocks: taken one at a time from a global counter, size classes largest first (blend_fwd
-  // filed every non-empty block under the half-octave of its candidate count): greedy list scheduling over a
-  // nearly sorted list, so the warps finish within one small block of each other ----
+  // ---- a ring's blocks: taken one at a time from a global counter, size classes largest first (blend_fwd
+  // filed every non-empty block under the half-octave of its list length): greedy list scheduling over a
+  // nearly sorted list, so the rings finish within one small block of each other ----
   // s_pre[k] = number of blocks in the k largest classes
   {
     const uint32_t c = cls_count[RING_CLASSES - 1 - lane];
@@ -256,7 +257,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       }
     }
     {
-      // assignment of epoch m+2 and its candidate positions (consumed at the next boundary)
+      // assignment of epoch m+2 and its list positions (consumed at the next boundary)
       uint32_t a_addr, a_flag;
       const uint32_t real_p2 = assign(m + 2, a_addr, a_flag, nbA);
       validA = a_addr != 0xffffffffu;
@@ -267,7 +268,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     }
     if (m < 0) continue;
 
-    // ================= the 32 steps of period m =================
+    // ================= the 16 steps of period m =================
     const uint32_t stA_addr = smem_u32(&rw.eA[m & 1][lane]), stB_addr = smem_u32(&rw.eB[m & 1][lane]);
     const uint32_t snap_addr = smem_u32(&rw.snap[lane][0]);
     const uint32_t zero_addr = smem_u32(&rw.zero);
@@ -281,7 +282,7 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       pyf = __shfl_sync(FULL, pyf, src);
       if (has_bg) Tf = __shfl_sync(FULL, Tf, src);
       {
-        // pixel 0 arrives at lane u: its previous element has seen all 32 pixels. One lane per step takes this
+        // pixel 0 arrives at lane u of each ring: its previous element has seen all 16 pixels. One lane per ring and step takes this
         // path, so it is written as predicated vector accesses straight from / into the registers that hold the sums
         // and the element (a branch plus compiler-chosen temporaries costs 8 more issue slots per step).
         asm volatile(
