@@ -31,7 +31,10 @@
 
 namespace cg {
 
-constexpr int RING_WARPS = 4;     // per CTA; warps are independent
+#ifndef CG_RING_WARPS
+#define CG_RING_WARPS 4
+#endif
+constexpr int RING_WARPS = CG_RING_WARPS;     // per CTA; warps are independent
 #ifndef CG_RING_CTAS
 #define CG_RING_CTAS 6
 #endif
@@ -272,6 +275,28 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
     const uint32_t stA_addr = smem_u32(&rw.eA[m & 1][lane]), stB_addr = smem_u32(&rw.eB[m & 1][lane]);
     const uint32_t snap_addr = smem_u32(&rw.snap[lane][0]);
     const uint32_t zero_addr = smem_u32(&rw.zero);
+    // The element switch: pixel 0 arrives at lane u of each ring at step u, when that lane's previous element has seen
+    // all 16 pixels. One lane per ring and step takes this path, so it is written as predicated vector accesses
+    // straight from / into the registers that hold the sums and the element (a branch plus compiler-chosen
+    // temporaries costs 8 more issue slots per step). It is issued at the END of the step before (for lane 0: ahead of
+    // the loop), so that the latency of its loads runs under the next step's shuffles instead of in front of the
+    // first use of the element.
+#define RING_SWITCH(WHICH)                                                                                        \
+    asm volatile(                                                                                                  \
+        "{\n\t.reg .pred sw;\n\t"                                                                                 \
+        "setp.eq.u32 sw, %16, %17;\n\t"                                                                            \
+        "@sw st.shared.v4.f32 [%18], {%8, %9, %10, %11};\n\t"                                                      \
+        "@sw st.shared.v4.f32 [%18+16], {%12, %13, %14, %15};\n\t"                                                 \
+        "@sw st.shared.v4.f32 [%18+32], {%4, %5, %6, %7};\n\t"                                                     \
+        "@sw ld.shared.v4.f32 {%0, %1, %2, %3}, [%19];\n\t"                                                        \
+        "@sw ld.shared.v4.f32 {%4, %5, %6, %7}, [%20];\n\t"                                                        \
+        "@sw ld.shared.v4.f32 {%8, %9, %10, %11}, [%21];\n\t" /* (zeros: two loads instead of seven moves) */      \
+        "@sw ld.shared.v4.f32 {%12, %13, %14, %15}, [%21];\n\t}"                                                   \
+        : "+f"(ex), "+f"(ey), "+f"(eo), "+f"(col), "+f"(ca), "+f"(cb), "+f"(cc), "+f"(poswf),                      \
+          "+f"(S0), "+f"(S1), "+f"(S2), "+f"(S3), "+f"(S4), "+f"(S5), "+f"(S7), "+f"(spad)                         \
+        : "r"(hl), "r"(WHICH), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr), "r"(zero_addr)                        \
+        : "memory")
+    RING_SWITCH(0u);
 #pragma unroll RING_UNROLL
     for (uint32_t u = 0; u < uint32_t(RING_LANES); ++u) {
       T = __shfl_sync(FULL, T, src);
@@ -281,25 +306,6 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
       pxf = __shfl_sync(FULL, pxf, src);
       pyf = __shfl_sync(FULL, pyf, src);
       if (has_bg) Tf = __shfl_sync(FULL, Tf, src);
-      {
-        // pixel 0 arrives at lane u of each ring: its previous element has seen all 16 pixels. One lane per ring and step takes this
-        // path, so it is written as predicated vector accesses straight from / into the registers that hold the sums
-        // and the element (a branch plus compiler-chosen temporaries costs 8 more issue slots per step).
-        asm volatile(
-            "{\n\t.reg .pred sw;\n\t"
-            "setp.eq.u32 sw, %16, %17;\n\t"
-            "@sw st.shared.v4.f32 [%18], {%8, %9, %10, %11};\n\t"
-            "@sw st.shared.v4.f32 [%18+16], {%12, %13, %14, %15};\n\t"
-            "@sw st.shared.v4.f32 [%18+32], {%4, %5, %6, %7};\n\t"
-            "@sw ld.shared.v4.f32 {%0, %1, %2, %3}, [%19];\n\t"
-            "@sw ld.shared.v4.f32 {%4, %5, %6, %7}, [%20];\n\t"
-            "@sw ld.shared.v4.f32 {%8, %9, %10, %11}, [%21];\n\t"      // (zeros: two loads instead of seven moves)
-            "@sw ld.shared.v4.f32 {%12, %13, %14, %15}, [%21];\n\t}"
-            : "+f"(ex), "+f"(ey), "+f"(eo), "+f"(col), "+f"(ca), "+f"(cb), "+f"(cc), "+f"(poswf),
-              "+f"(S0), "+f"(S1), "+f"(S2), "+f"(S3), "+f"(S4), "+f"(S5), "+f"(S7), "+f"(spad)
-            : "r"(hl), "r"(u), "r"(snap_addr), "r"(stA_addr), "r"(stB_addr), "r"(zero_addr)
-            : "memory");
-      }
       const uint32_t posw = __float_as_uint(poswf);
       if (posw & 0x80000000u) {
         // first element of its block (back to front): the arriving slot becomes pixel p of that block
@@ -339,7 +345,9 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
         S5 = fmaf(qy, dy, S5);
         S7 = fmaf(w, dLp, S7);
       }
+      RING_SWITCH(u + 1u);   // (no lane matches after the last step: lane 0 switches after the epoch boundary)
     }
+#undef RING_SWITCH
   }
   // the last warp to leave re-arms the two counters for the next launch over the same forward state
   if (lane == 0) {
