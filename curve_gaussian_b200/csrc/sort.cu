@@ -251,6 +251,110 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
   CG_SORT_TICK(6);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small sorts (n <= SMALL_TILE pairs, e.g. the depth sort of a 5 k-Gaussian scene): ALL passes in one CTA. The keys
+// never leave the SM between passes: rank (same stable match.any ranking as the onesweep pass), scatter into
+// shared memory, read back in sorted order, next digit. One launch instead of histogram + scan + one launch per
+// pass, each of which costs 8-10 us at this size because of launch latency and the look-back machinery alone.
+constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_ITEMS = 16;
+constexpr int SMALL_TILE = SMALL_THREADS * SMALL_ITEMS;   // 8192 pairs
+template <typename K>
+struct SmallSortSmem {
+  K keys[SMALL_TILE];
+  uint32_t vals[SMALL_TILE];
+  uint32_t whist[SMALL_THREADS / 32][257];
+  uint32_t local_start[256];
+  uint32_t wsum[SMALL_THREADS / 32];
+};
+
+template <typename K>
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+sort_small(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
+           uint32_t* __restrict__ vals_out, int64_t R, const uint32_t* __restrict__ d_n, int passes, int bpp) {
+  pdl_wait();
+  if (d_n) R = min(R, int64_t(*d_n));
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallSortSmem<K>& s = *reinterpret_cast<SmallSortSmem<K>*>(smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int WARPS = SMALL_THREADS / 32;
+  const uint32_t dmask = (1u << bpp) - 1u;
+  const int64_t warp_base = int64_t(warp) * (32 * SMALL_ITEMS);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  K k[SMALL_ITEMS];
+  uint32_t v[SMALL_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SMALL_ITEMS; ++i) {
+    const int64_t idx = warp_base + i * 32 + lane;
+    const bool ok = idx < R;
+    k[i] = ok ? keys_in[idx] : K(~K(0));
+    v[i] = ok ? vals_in[idx] : 0u;
+  }
+  for (int p = 0; p < passes; ++p) {
+    const int shift = bpp * p;
+    for (int i = tid; i < WARPS * 257; i += SMALL_THREADS) (&s.whist[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t* wh = s.whist[warp];
+    uint16_t rank[SMALL_ITEMS];
+#pragma unroll
+    for (int h = 0; h < SMALL_ITEMS; h += 8) {
+      uint32_t m[8], old[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t idx = warp_base + (h + i) * 32 + lane;
+        const uint32_t d = (idx < R) ? (uint32_t(k[h + i] >> shift) & dmask) : 256u;
+        m[i] = __match_any_sync(0xffffffffu, d);
+        old[i] = 0;
+        if (lane == uint32_t(__ffs(int(m[i])) - 1)) old[i] = atomicAdd(&wh[d], uint32_t(__popc(m[i])));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t base = __shfl_sync(0xffffffffu, old[i], __ffs(int(m[i])) - 1);
+        rank[h + i] = uint16_t(base + __popc(m[i] & lt_mask));
+      }
+    }
+    __syncthreads();
+    if (tid < 256) {
+      // digit tid: exclusive scan of its counts across the warps, then of the digit totals across the digits
+      uint32_t total = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) { const uint32_t c = s.whist[w][tid]; s.whist[w][tid] = total; total += c; }
+      uint32_t inc = total;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= uint32_t(o)) inc += n; }
+      if (lane == 31) s.wsum[warp] = inc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint32_t wb = 0;
+      for (uint32_t i = 0; i < warp; ++i) wb += s.wsum[i];
+      s.local_start[tid] = wb + inc - total;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SMALL_ITEMS; ++i) {
+      const int64_t idx = warp_base + i * 32 + lane;
+      if (idx < R) {
+        const uint32_t d = uint32_t(k[i] >> shift) & dmask;
+        const uint32_t pos = s.local_start[d] + s.whist[warp][d] + rank[i];
+        s.keys[pos] = k[i];
+        s.vals[pos] = v[i];
+      }
+    }
+    __syncthreads();
+    if (p + 1 < passes) {
+#pragma unroll
+      for (int i = 0; i < SMALL_ITEMS; ++i) {
+        const int64_t idx = warp_base + i * 32 + lane;
+        if (idx < R) { k[i] = s.keys[idx]; v[i] = s.vals[idx]; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int64_t j = tid; j < R; j += SMALL_THREADS) {
+    keys_out[j] = s.keys[j];
+    vals_out[j] = s.vals[j];
+  }
+}
+
 }  // namespace
 
 // Digit geometry of a sort of `end_bit` key bits: number of passes and (equal) bits per pass
@@ -294,6 +398,31 @@ int radix_sort_pairs(const SortBufs<K>& b, int64_t R, int end_bit, int* out_buf,
   const uint32_t dmask = (1u << bpp) - 1u;
   const int64_t ntiles = (R + SORT_TILE - 1) / SORT_TILE;
 
+  if (R <= SMALL_TILE) {
+    // the whole sort in one CTA (the digit histograms a producer may have prepared are not needed)
+    static thread_local bool small_attr[64] = {false};
+    int sdev = 0;
+    CG_CUDA(cudaGetDevice(&sdev));
+    CG_ARG(sdev >= 0 && sdev < 64, "device ordinal");
+    if (!small_attr[sdev]) {
+      CG_CUDA(cudaFuncSetAttribute(sort_small<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(SmallSortSmem<K>))));
+      small_attr[sdev] = true;
+    }
+    const int res = passes & 1;   // where the multi-pass sort would leave the result
+    if (hist_ready) {
+      // the producer's digit counts become exclusive bases, as after the multi-pass sort (the super-tile binning reads
+      // its spans from them)
+      count_launches(1);
+      launch_k(sort_scan_bins, dim3(passes), dim3(256), 0, stream, b.hist);
+      CG_LAUNCH_CHECK(debug, stream);
+    }
+    count_launches(1);
+    launch_k(sort_small<K>, dim3(1), dim3(SMALL_THREADS), sizeof(SmallSortSmem<K>), stream, b.keys[0], b.vals[0], b.keys[res],
+             final_vals ? final_vals : b.vals[res], R, d_n, passes, bpp);
+    CG_LAUNCH_CHECK(debug, stream);
+    *out_buf = res;
+    return CG_OK;
+  }
   // (per device: a process that drives several GPUs sets the attribute on each of them)
   static thread_local bool attr_set[64] = {false};
   int dev = 0;
