@@ -256,9 +256,9 @@ bin_fill(uint32_t ns, uint32_t sgx, int grid_x, int grid_y, const uint2* __restr
          const uint32_t* __restrict__ cbase, const uint2* __restrict__ ranges, uint32_t cap,
          uint32_t* __restrict__ point_list) {
   pdl_wait();
-  __shared__ uint32_t s_stage[BIN_STAGE];
-  __shared__ uint8_t s_tile[BIN_STAGE];
+  __shared__ uint16_t s_stage[BIN_STAGE];   // tile (6 bits) << 10 | copy index inside the chunk (10 bits)
   __shared__ uint32_t s_id[8][BIN_WCHUNK];
+  static_assert(BIN_CHUNK <= 1024, "a staged entry holds a 10-bit copy index");
   __shared__ uint32_t s_wcnt[8][64];     // per warp and tile: count, then offset inside the tile's run
   __shared__ uint32_t s_loff[65];        // first staged slot of each tile
   __shared__ uint32_t s_goff[64];        // global position of staged slot i of tile t = s_goff[t] + i
@@ -309,14 +309,14 @@ bin_fill(uint32_t ns, uint32_t sgx, int grid_x, int grid_y, const uint2* __restr
     while (a) {
       const uint32_t k = uint32_t(__ffs(int(a))) - 1u;
       a &= a - 1u;
-      if (staged) { s_stage[p0] = ids[k]; s_tile[p0] = uint8_t(lane); }
+      if (staged) s_stage[p0] = uint16_t((lane << 10) | (warp * BIN_WCHUNK + e * 32 + k));
       else if (g0 + p0 < cap) point_list[g0 + p0] = ids[k];
       ++p0;
     }
     while (b) {
       const uint32_t k = uint32_t(__ffs(int(b))) - 1u;
       b &= b - 1u;
-      if (staged) { s_stage[p1] = ids[k]; s_tile[p1] = uint8_t(32u + lane); }
+      if (staged) s_stage[p1] = uint16_t(((32u + lane) << 10) | (warp * BIN_WCHUNK + e * 32 + k));
       else if (g1 + p1 < cap) point_list[g1 + p1] = ids[k];
       ++p1;
     }
@@ -324,8 +324,9 @@ bin_fill(uint32_t ns, uint32_t sgx, int grid_x, int grid_y, const uint2* __restr
   __syncthreads();
   if (staged) {
     for (uint32_t i = threadIdx.x; i < n_inst; i += 256) {
-      const uint32_t g = s_goff[s_tile[i]] + i;
-      if (g < cap) point_list[g] = s_stage[i];
+      const uint32_t en = s_stage[i];
+      const uint32_t g = s_goff[en >> 10] + i;
+      if (g < cap) point_list[g] = (&s_id[0][0])[en & 1023u];
     }
   }
   __syncthreads();   // (the shared arrays are rewritten by the next chunk)

@@ -731,7 +731,7 @@ int launch_fwd_blend(const cg_raster_settings* s, int64_t P, int64_t R, void* ge
     launch_k(bin_count, dim3(min(cb, 148u * 8u)), dim3(256), 0, st, ns, uint32_t(sgx), im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect, bs.ccnt);
     launch_k(bin_scan_chunks, dim3(ns), dim3(64), 0, st, uint32_t(sgx), gx, gy, im.chunk_start, bs.ccnt, bs.cbase, im.tile_cnt);
     launch_k(bin_scan_tiles_order, dim3(1), dim3(1024), 0, st, uint32_t(tiles), im.tile_cnt, uint32_t(R), im.ranges, im.tile_order);
-    launch_k(bin_fill, dim3(min(cb, 148u * 4u)), dim3(256), 0, st, ns, uint32_t(sgx), gx, gy, im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect,
+    launch_k(bin_fill, dim3(min(cb, 148u * 8u)), dim3(256), 0, st, ns, uint32_t(sgx), gx, gy, im.st_ranges, im.chunk_start, bs.is.vals[cur], g.rect,
              bs.cbase, im.ranges, uint32_t(R), bk.point_list); }
     CG_LAUNCH_CHECK(s->debug, st);
   } else if (R > 0) {
