@@ -99,12 +99,14 @@ sort_onesweep_pass(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
 
   // Dynamic tile id: a tile only ever waits on tiles that already started.
   if (tid == 0) s.tile_id = atomicAdd(ticket, 1u);
-  for (int i = tid; i < WARPS * 257; i += SORT_THREADS) (&s.whist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s.tile_id;
   CG_SORT_TICK(0);
   const int64_t tile_base = int64_t(tile) * SORT_TILE;
+  // (surplus CTAs of a grid sized for a capacity leave before they touch anything else)
   if (tile_base >= R) return;   // uniform: tickets are handed out in order, so every live tile's predecessors are live
+  for (int i = tid; i < WARPS * 257; i += SORT_THREADS) (&s.whist[0][0])[i] = 0;
+  __syncthreads();
   const int64_t warp_base = tile_base + int64_t(warp) * (32 * SORT_ITEMS);
 
   K k[SORT_ITEMS];
