@@ -164,7 +164,10 @@ __device__ __forceinline__ bool block_candidate(float cx, float cy, float A, flo
 
 // Radix sort geometry (see sort.cu).
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
+#ifndef CG_SORT_ITEMS
+#define CG_SORT_ITEMS 16
+#endif
+constexpr int SORT_ITEMS = CG_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
 constexpr int SORT_MAX_PASSES = 8;
 

@@ -395,3 +395,16 @@ def test_sort_path_binning_matches_golden():
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_raster_golden.py", "-q", "-m", "gpu", "-x"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_lane_per_pixel_colour_backward_in_child_process():
+    """CURVEGS_BWD_RING=0 sends the colour-only blend backward (the training path) through the lane-per-pixel kernel
+    instead of the ring kernel; the switch is read once per process, so the end-to-end pipeline tests (which compare
+    the whole step's gradients with the CPU oracle) run in a child process with it."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CURVEGS_BWD_RING="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_render_pipeline.py", "-q", "-m", "gpu", "-x"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
