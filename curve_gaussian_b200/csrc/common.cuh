@@ -289,15 +289,16 @@ struct BinKeep {
   }
 };
 
-// Binning sorts twice:
+// Binning (binning.cuh) orders the Gaussians once and never sorts the R tile instances:
 //   GeomState::gs: the P Gaussians sorted by the bits of their view-space depth (value = Gaussian index);
 //                  runs inside cg_raster_fwd_geom, overlapping the host's wait for R
-//   BinScratch::is (forward-only scratch): the R tile-instances, emitted in that depth order, sorted by
-//                  tile index only
-// A stable sort by tile of a list that is already in (depth, index) order is the
-// (tile, depth) order with ties in emission = index order, i.e. exactly the permutation the
-// reference gets from one 64-bit sort of tile<<32|depth (rasterizer_impl.cu:70-111, :309-314),
-// but the big R-sized passes shrink from 6 x 24 B to 2 x 16 B per instance.
+//   BinScratch::is (forward-only scratch): one copy of a Gaussian per 8x8-tile super-tile it overlaps, emitted in
+//                  that depth order and stably sorted by super-tile index (one small pass); the per-tile lists are
+//                  then filled by counting (ccnt / cbase)
+// A tile's list is therefore in (depth, index) order, i.e. exactly the permutation the reference gets from one 64-bit
+// sort of tile<<32|depth over the R instances (rasterizer_impl.cu:70-111, :309-314).
+// With CURVEGS_BINNING=sort `is` holds the R (tile, id) instances instead, emitted in depth order and stably sorted
+// by tile index only (two 16-byte passes over R): the round-1 path, kept as fallback and yardstick.
 struct BinScratch {
   SortBufs<uint32_t> is;
   // super-tile binning (binning.cuh): per chunk of BIN_CHUNK copies and tile of its super-tile

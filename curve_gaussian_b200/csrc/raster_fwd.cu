@@ -1,6 +1,7 @@
-// Forward rasterization kernels: EWA preprocess (+tile counts, block sums),
-// block-sum scan, key emission, tile ranges, sorted-record gather, and the
-// per-tile front-to-back blend fed by TMA bulk copies.
+// Forward rasterization kernels: EWA preprocess (+tile counts, block sums, depth-sort keys), block-sum scans,
+// emission of (super-tile, Gaussian) copies or (tile, Gaussian) instances, tile ranges, and the per-tile
+// front-to-back blend (TMA bulk copies of the tile's id list, per-record async gathers). The tile binning itself
+// is in binning.cuh, the radix sort in sort.cu.
 //
 // Reference behaviour followed (semantics, not structure):
 //   preprocess   forward.cu:155-274, auxiliary.h:40-55,151-176
