@@ -127,7 +127,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
 }
 
 // Single CTA: exclusive scan of the per-block sums, total -> g.total[0].
-__global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState g, int slot) {
+__global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState g, int slot, uint32_t* __restrict__ host_out) {
   pdl_wait();
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
@@ -159,7 +159,13 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
     if (threadIdx.x == 1023) s_carry = carry + s_w[w] + inc;
     __syncthreads();
   }
-  if (threadIdx.x == 0) g.total[slot] = s_carry;
+  if (threadIdx.x == 0) {
+    g.total[slot] = s_carry;
+    // the host's copy of R: stored straight into mapped pinned memory (no copy-engine operation between this kernel
+    // and the event the host waits on; a D2H copy would also queue behind whatever bulk D2H traffic the application has
+    // in flight on other streams)
+    if (host_out) { *reinterpret_cast<volatile uint32_t*>(host_out) = s_carry; __threadfence_system(); }
+  }
 }
 
 // Block sums of tiles_touched (shift = 0) or of the number of super-tiles overlapped (shift = ST_SHIFT), taken in
@@ -642,28 +648,27 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
                                                  s->tanfovy, fx, fy, gx, gy, s->antialiasing, colors,
                                                  s->render_geo ? all_map : nullptr, radii, g); }
   CG_LAUNCH_CHECK(s->debug, st);
-  { StageTimer t_(ST_SCAN, st, 1);
-  launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g, 0); }
-  CG_LAUNCH_CHECK(s->debug, st);
-  // R goes to pinned host memory; the host then waits on an EVENT recorded right behind that copy while the
-  // stream already carries the next, R-independent stage (depth sort of the Gaussians + offsets in depth
-  // order), so the wake-up latency of the host is hidden behind ~0.1 ms of useful GPU work.
+  // R goes to pinned host memory (written by the scan kernel itself); the host then waits on an EVENT recorded right
+  // behind that kernel while the stream already carries the next, R-independent stage (depth sort of the Gaussians +
+  // offsets in depth order), so the wake-up latency of the host is hidden behind ~0.1 ms of useful GPU work.
   // (num_rendered == NULL: capacity mode, R stays on the device and nothing here touches the host)
   int dev = 0;
   static thread_local uint32_t* h_total[64] = {nullptr};
+  static thread_local uint32_t* h_total_dev[64] = {nullptr};   // device-side address of the same mapped allocation
   static thread_local cudaEvent_t h_event[64] = {nullptr};
   if (num_rendered) {
     CG_CUDA(cudaGetDevice(&dev));
     CG_ARG(dev >= 0 && dev < 64, "device ordinal");
   }
   if (num_rendered && !h_total[dev]) {
-    CG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_total[dev]), 64, cudaHostAllocDefault));
+    CG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_total[dev]), 64, cudaHostAllocMapped));
+    CG_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_total_dev[dev]), h_total[dev], 0));
     CG_CUDA(cudaEventCreateWithFlags(&h_event[dev], cudaEventDisableTiming));
   }
-  if (num_rendered) {
-    CG_CUDA(cudaMemcpyAsync(h_total[dev], g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CG_CUDA(cudaEventRecord(h_event[dev], st));
-  }
+  { StageTimer t_(ST_SCAN, st, 1);
+  launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g, 0, num_rendered ? h_total_dev[dev] : static_cast<uint32_t*>(nullptr)); }
+  CG_LAUNCH_CHECK(s->debug, st);
+  if (num_rendered) CG_CUDA(cudaEventRecord(h_event[dev], st));
   {
     int rc, gcur = 0;
     { StageTimer t_(ST_SORT, st, 0);
@@ -674,7 +679,7 @@ int launch_fwd_geom(const cg_raster_settings* s, int64_t P, const float* means3D
     // super-tile copies (total -> g.total[1])
     const bool by_st = bin_by_supertile(W, H);
     launch_k(perm_block_sums, dim3(unsigned(nblk)), dim3(256), 0, st, P, g.gs.vals[gcur], g, by_st ? ST_SHIFT : 0);
-    launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g, by_st ? 1 : 0); }
+    launch_k(scan_block_sums, dim3(1), dim3(1024), 0, st, nblk, g, by_st ? 1 : 0, static_cast<uint32_t*>(nullptr)); }
     CG_LAUNCH_CHECK(s->debug, st);
   }
   if (num_rendered) {
