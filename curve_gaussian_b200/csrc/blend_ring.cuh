@@ -86,7 +86,7 @@ __device__ __forceinline__ float ring_div(float a, float d) {
 
 __global__ void __launch_bounds__(RING_WARPS * 32, CG_RING_CTAS)
 blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cls_count,
-               const uint32_t* __restrict__ cls_list, uint32_t nblocks, uint32_t* __restrict__ work,
+               const uint4* __restrict__ cls_list, uint32_t nblocks, uint32_t* __restrict__ work,
                const uint32_t* __restrict__ blk_cnt, int grid_x,
                const Rec* __restrict__ grec, const uint32_t* __restrict__ cand, const uint32_t* __restrict__ cand_id,
                int W, int H, float ddelx_dx, float ddely_dy, const float* __restrict__ bg,
@@ -139,11 +139,10 @@ blend_bwd_ring(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cl
 #pragma unroll
       for (uint32_t step = RING_CLASSES / 2; step > 0; step >>= 1)
         if (rw.pre[k + step] <= at) k += step;
-      q_bid = cls_list[size_t(RING_CLASSES - 1 - k) * nblocks + (at - rw.pre[k])];
-      q_cnt = blk_cnt[q_bid];
-      const uint2 r = ranges[q_bid >> 4];
-      q_rx = r.x;
-      q_len = r.y - r.x;
+      // one 16-byte descriptor (written by blend_fwd when it filed the block): a chain of three dependent loads
+      // (block id -> count, tile -> range) stalled the whole warp inside this function
+      const uint4 d = cls_list[size_t(RING_CLASSES - 1 - k) * nblocks + (at - rw.pre[k])];
+      q_bid = d.x; q_cnt = d.y; q_rx = d.z; q_len = d.w;
     }
   };
   if (hl < 4) load_meta(int(hl));

@@ -242,7 +242,9 @@ struct ImgState {
   uint32_t* cls_count;  // [RING_CLASSES] non-empty blocks per size class (class = half-octave of blk_cnt), then
                         // [RING_CLASSES], [RING_CLASSES + 1] = work / exit counters of blend_bwd_ring (left at zero by it);
                         // zero-filled together with `ranges` at the start of every forward
-  uint32_t* cls_list;   // [RING_CLASSES][tiles * 16] block ids per class, in arrival order
+  uint4* cls_list;      // [RING_CLASSES][tiles * 16] block descriptors per class, in arrival order:
+                        // {block id, list length, tile range start, tile range length} - everything the ring backward
+                        // needs to walk the block, in one 16-byte load
   // super-tile binning (binning.cuh); tile_cnt and st_ranges are zero-filled with `ranges`
   uint32_t* tile_cnt;    // [tiles] instances per tile
   uint2* st_ranges;      // [super-tiles] span of each super-tile in the sorted copy list
@@ -263,7 +265,7 @@ struct ImgState {
     s.tile_maxc = c.take<uint32_t>(tiles * BLEND_SUBS);
     s.tile_order = c.take<uint32_t>(tiles * BLEND_SUBS);
     s.blk_cnt = c.take<uint32_t>(tiles * 16);
-    s.cls_list = c.take<uint32_t>(size_t(RING_CLASSES) * tiles * 16);
+    s.cls_list = c.take<uint4>(size_t(RING_CLASSES) * tiles * 16);
     if (bytes) *bytes = (c.used + 127) & ~size_t(127);
     return s;
   }

@@ -412,7 +412,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
           const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_invd,
           float* __restrict__ out_map, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
           uint32_t* __restrict__ tile_maxc, uint32_t* __restrict__ cand_lists, uint32_t* __restrict__ cand_ids,
-          uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ cls_count, uint32_t* __restrict__ cls_list,
+          uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ cls_count, uint4* __restrict__ cls_list,
           uint32_t nblocks) {
   pdl_wait();
   __shared__ __align__(128) Rec s_rec[2][BATCH];
@@ -608,7 +608,7 @@ blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_or
     if (n) {
       const uint32_t msb = 31u - uint32_t(__clz(int(n)));
       const uint32_t cls = min(uint32_t(RING_CLASSES - 1), 2u * msb + (msb ? ((n >> (msb - 1u)) & 1u) : 0u));
-      cls_list[size_t(cls) * nblocks + atomicAdd(&cls_count[cls], 1u)] = bid;
+      cls_list[size_t(cls) * nblocks + atomicAdd(&cls_count[cls], 1u)] = make_uint4(bid, n, range.x, uint32_t(total));
     }
   }
   __syncthreads();
