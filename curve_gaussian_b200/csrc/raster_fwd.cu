@@ -46,6 +46,7 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
 
   const int64_t idx = blk0 + threadIdx.x;
   uint32_t touched = 0, depth_key = 0xffffffffu;
+  uint2 rect_out = make_uint2(0u, 0u);   // (an empty rect for a culled Gaussian: the binning reads the rect alone)
   int radius_out = 0;
   if (idx < P) {
     const float px = s_mean[3 * threadIdx.x], py = s_mean[3 * threadIdx.x + 1], pz = s_mean[3 * threadIdx.x + 2];
@@ -103,12 +104,13 @@ preprocess_fwd(int64_t P, const float* __restrict__ means3D, const float* __rest
           rec[0] = make_float4(conic.x, conic.y, conic.z, 1.f / p_view.z);
           rec[1] = make_float4(pix_x, pix_y, __ldg(opacities + idx) * h_scaling, colors ? __ldg(colors + idx) : 0.f);
           rec[2] = all_map ? __ldg(reinterpret_cast<const float4*>(all_map) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-          g.rect[idx] = make_uint2(uint32_t(mnx) | (uint32_t(mny) << 16), uint32_t(mxx) | (uint32_t(mxy) << 16));
+          rect_out = make_uint2(uint32_t(mnx) | (uint32_t(mny) << 16), uint32_t(mxx) | (uint32_t(mxy) << 16));
         }
       }
     }
     radii[idx] = radius_out;
     g.tiles[idx] = touched;
+    g.rect[idx] = rect_out;
     // input of the depth sort: key = bits of the view-space depth (culled Gaussians emit nothing, their key only
     // has to be deterministic), value = Gaussian index
     g.gs.keys[0][idx] = depth_key;
@@ -134,10 +136,15 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int64_t base = 0; base < nblk; base += 1024) {
-    int64_t i = base + threadIdx.x;
-    uint32_t v = (i < nblk) ? g.blk_sum[i] : 0u;
-    uint32_t inc = v;
+  // four consecutive sums per thread: the ~3900 block sums of a 1 M-Gaussian scene are one trip of the loop (this
+  // kernel is on the path to the host's copy of R)
+  for (int64_t base = 0; base < nblk; base += 4096) {
+    const int64_t i0 = base + int64_t(threadIdx.x) * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < nblk) ? g.blk_sum[i0 + k] : 0u;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = mine;
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += n;
@@ -154,9 +161,14 @@ __global__ void __launch_bounds__(1024) scan_block_sums(int64_t nblk, GeomState 
     }
     __syncthreads();
     const uint32_t carry = s_carry;
-    if (i < nblk) g.blk_prefix[i] = carry + s_w[w] + inc - v;
+    uint32_t run = carry + s_w[w] + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < nblk) g.blk_prefix[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + s_w[w] + inc;
+    if (threadIdx.x == 1023) s_carry = run;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -178,8 +190,9 @@ perm_block_sums(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int s
   uint32_t v = 0;
   if (i < P) {
     const uint32_t idx = perm[i];
-    v = g.tiles[idx];
-    if (shift && v) v = rect_area(st_rect(g.rect[idx], shift));   // super-tiles overlapped instead of tiles
+    // (one gather behind perm[i], not two: a culled Gaussian has an empty rect, and a rect's area is its tile count)
+    const uint2 rc = g.rect[idx];
+    v = rect_area(shift ? st_rect(rc, shift) : rc);   // tiles, or super-tiles, overlapped
   }
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) s_wsum[threadIdx.x >> 5] = v;
@@ -223,12 +236,12 @@ emit_keys(int64_t P, const uint32_t* __restrict__ perm, GeomState g, int grid_x,
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t idx = (i < P) ? perm[i] : 0u;
-  uint32_t cnt = (i < P) ? g.tiles[idx] : 0u;
   uint2 my_rect = make_uint2(0u, 0u);
-  if (cnt) {
-    my_rect = g.rect[idx];
-    if (shift) { my_rect = st_rect(my_rect, shift); cnt = rect_area(my_rect); }   // (grid_x is then in super-tiles)
+  if (i < P) {
+    my_rect = g.rect[idx];                                   // (empty for a culled Gaussian)
+    if (shift) my_rect = st_rect(my_rect, shift);            // (grid_x is then in super-tiles)
   }
+  const uint32_t cnt = rect_area(my_rect);
   uint32_t inc = cnt;
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
