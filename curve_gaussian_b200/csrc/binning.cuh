@@ -192,12 +192,13 @@ bin_scan_chunks(uint32_t sgx, int grid_x, int grid_y, const uint32_t* __restrict
   const uint32_t c0 = chunk_start[s], c1 = chunk_start[s + 1];
   if (c0 == c1) return;   // (tile_cnt is zero-filled)
   uint32_t run = 0;
-  for (uint32_t c = c0; c < c1; c += 4) {
-    uint32_t v[4];
+  // (16 independent loads per round trip: the kernel is as long as the chain of the largest super-tile)
+  for (uint32_t c = c0; c < c1; c += 16) {
+    uint32_t v[16];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (c + k < c1) ? ccnt[size_t(c + k) * 64 + t] : 0u;
+    for (int k = 0; k < 16; ++k) v[k] = (c + k < c1) ? ccnt[size_t(c + k) * 64 + t] : 0u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 16; ++k) {
       if (c + k < c1) cbase[size_t(c + k) * 64 + t] = run;
       run += v[k];
     }
