@@ -41,15 +41,26 @@ struct LossParams {
 // torch.clamp(x, 0, 1) including its NaN behaviour (NaN stays NaN)
 __device__ __forceinline__ float clamp01f(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
-__device__ __forceinline__ double block_sum_d(double v, double* s_red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+// Four fp64 block sums at once; the totals end in threads 0..3 (sum t in thread t). The first two butterfly steps halve
+// the number of values a lane still carries (lanes keep sums {0,1} or {2,3}, then one of the pair): 12 SHFLs and 6
+// DADDs per warp instead of 40 and 20 for four plain butterflies, and one barrier instead of eight. s_red: NT/32 x 4.
+__device__ __forceinline__ double block_sum4_d(double (&v)[4], double* s_red) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool h4 = (lane & 16u) != 0u, h3 = (lane & 8u) != 0u;
+  double k0 = h4 ? v[2] : v[0], k1 = h4 ? v[3] : v[1];
+  k0 += __shfl_xor_sync(0xffffffffu, h4 ? v[0] : v[2], 16);
+  k1 += __shfl_xor_sync(0xffffffffu, h4 ? v[1] : v[3], 16);
+  double k = h3 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, h3 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  if ((lane & 7u) == 0u) s_red[warp * 4 + (lane >> 3)] = k;   // lanes 0, 8, 16, 24 hold the warp's sums 0..3
   __syncthreads();
   double t = 0.0;
-  if (threadIdx.x == 0)
-    for (int i = 0; i < NT / 32; ++i) t += s_red[i];
-  return t;  // valid on thread 0
+  if (threadIdx.x < 4)
+    for (int w = 0; w < NT / 32; ++w) t += s_red[w * 4 + threadIdx.x];
+  return t;   // valid on threads 0..3
 }
 
 // stats block of the LOSS variant (8 doubles, zeroed by the launcher):
@@ -64,7 +75,7 @@ ssim_fwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, co
   __shared__ float s1[IN][IN + 1];
   __shared__ float s2[IN][IN + 1];
   __shared__ float hq[5][IN][TS + 1];   // +1: the RUN-strided stores of the horizontal pass stay conflict-free
-  __shared__ double s_red[NT / 32];
+  __shared__ double s_red[NT / 32 * 4];
   const size_t plane = size_t(blockIdx.z) * H * W;
   const float* a = img1 + plane;
   const float* b = img2 + plane;
@@ -153,15 +164,11 @@ ssim_fwd_kernel(int H, int W, LossParams prm, const float* __restrict__ img1, co
     }
   }
   if (LOSS) {
-    const double t0 = block_sum_d(a_ssim, s_red);
-    const double t1 = block_sum_d(a_pos, s_red);
-    const double t2 = block_sum_d(a_neg, s_red);
-    const double t3 = block_sum_d(a_cnt, s_red);
+    double part[4] = {a_ssim, a_pos, a_neg, a_cnt};
+    const double tsum = block_sum4_d(part, s_red);
+    if (threadIdx.x < 4) { atomicAdd(stats + threadIdx.x, tsum); __threadfence(); }
+    __syncwarp();
     if (threadIdx.x == 0) {
-      atomicAdd(stats + 0, t0);
-      atomicAdd(stats + 1, t1);
-      atomicAdd(stats + 2, t2);
-      atomicAdd(stats + 3, t3);
       __threadfence();
       const unsigned total = gridDim.x * gridDim.y;
       const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(stats + 4), 1u);
