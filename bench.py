@@ -362,9 +362,9 @@ def run_ours(a):
     alg_bytes = {
         "blend_bwd": 52 * (R or 0) + 32 * Npix + 48 * P,
         "blend_fwd": 52 * (R or 0) + 32 * Npix,
-        # depth sort of the P Gaussians (histogram read + 4 passes of 8-byte pairs r+w) and tile sort of the
-        # R instances (histogram read + 2 passes of 8-byte pairs r+w); radix_sort is timed per launch, so use R's
-        "radix_sort": (4 + 2 * 16) * (R or 0),
+        # depth sort of the P Gaussians (histogram read + 4 passes of 8-byte pairs r+w); the R instances are no longer
+        # sorted (super-tile binning), only ~0.18 R (super-tile, Gaussian) copies in one pass
+        "radix_sort": (4 + 4 * 16) * P + 16 * int(0.18 * (R or 0)),
         "preprocess_fwd": (44 + 36) * P,
         "preprocess_bwd": (76 + 40) * P,
     }
